@@ -1,0 +1,151 @@
+/* hannoy_b200.h — C-ABI of libhannoy_b200.so, the B200-native batched HNSW search engine that
+ * sits behind hannoy's Reader / QueryBuilder / Distance surface.
+ *
+ * hannoy (nnethercott/hannoy v0.1.3) has no FFI of its own: its boundary is the public Rust API
+ * (src/lib.rs:99-125).  Every entry point below names the reference interface it replaces;
+ * `file:line` is relative to the reference repository.  The Rust-side binding a maintainer would
+ * add is shown in INTEGRATION.md (crate source under rust/hannoy-b200/).
+ *
+ * Conventions
+ *  - plain pointers and sizes; no C++ / torch types; no exception crosses the boundary.
+ *  - every call returns hb_status; hb_last_error() gives a thread-local message for the last failure.
+ *  - caller owns all host buffers and they only need to live for the duration of the call;
+ *    the library owns all device memory.  Outputs are caller-allocated.
+ *  - an hb_index is immutable after hb_index_finalize (mirrors `Reader: Send + Sync` over an MVCC
+ *    snapshot); hb_search_* may be called concurrently from several host threads.
+ *  - results carry the ORIGINAL sparse ItemIds (u32), distances are the reference's f32 values.
+ *  - there is NO CPU fallback: without a CUDA device every compute call returns HB_ECUDA.
+ */
+#ifndef HANNOY_B200_H
+#define HANNOY_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hb_index hb_index; /* opaque */
+
+typedef enum {
+    HB_OK = 0,
+    HB_EINVAL = 1,             /* bad argument */
+    HB_EDIM = 2,               /* Error::InvalidVecDimension      src/error.rs, reader.rs:133-138 */
+    HB_EFORMAT = 3,            /* undecodable key/value           src/key.rs, src/node.rs:151-174 */
+    HB_ECUDA = 4,              /* CUDA runtime error / no device */
+    HB_ENOMEM = 5,
+    HB_ENCCL = 6,
+    HB_EMISSING_METADATA = 7,  /* Error::MissingMetadata          reader.rs:390-393 */
+    HB_EUNMATCHING_DISTANCE = 8, /* Error::UnmatchingDistance     reader.rs:400-405 */
+    HB_ENEED_BUILD = 9,        /* Error::NeedBuild                reader.rs:407-416 */
+    HB_ESTATE = 10             /* call order violated (e.g. search before finalize) */
+} hb_status;
+
+/* `D: Distance` (src/distance/mod.rs:26-48), identified by D::name() */
+typedef enum {
+    HB_EUCLIDEAN = 0,    /* "euclidean"                  src/distance/euclidean.rs  (squared L2) */
+    HB_COSINE = 1,       /* "cosine"                     src/distance/cosine.rs */
+    HB_MANHATTAN = 2,    /* "manhattan"                  src/distance/manhattan.rs */
+    HB_HAMMING = 3,      /* "hamming"                    src/distance/hamming.rs (codec Binary) */
+    HB_BQ_COSINE = 4,    /* "binary quantized cosine"    src/distance/binary_quantized_cosine.rs */
+    HB_BQ_EUCLIDEAN = 5, /* "binary quantized euclidean" src/distance/binary_quantized_euclidean.rs */
+    HB_BQ_MANHATTAN = 6  /* "binary quantized manhattan" src/distance/binary_quantized_manhattan.rs */
+} hb_metric;
+
+/* D::name() for a metric, and the reverse (returns -1 if unknown). */
+const char* hb_metric_name(hb_metric m);
+int hb_metric_from_name(const char* name);
+
+/* ---- Reader::open (src/reader.rs:387-431): snapshot an index out of the KV store ------------- */
+
+/* Start a snapshot of hannoy index `index` (the u16 key prefix, src/key.rs:19-23) for distance `m`. */
+hb_status hb_index_begin(hb_metric m, uint16_t index, hb_index** out);
+
+/* Route (a): feed raw LMDB pairs exactly as a heed cursor yields them (any order; pairs of other
+ * indexes are ignored).  Decodes KeyCodec (src/key.rs:54-82), NodeCodec Item/Links
+ * (src/node.rs:130-174), MetadataCodec (src/metadata.rs:49-73), VersionCodec (src/version.rs:48-59),
+ * Updated stones (src/update_status.rs) and the Roaring portable format (src/roaring.rs:14-32). */
+hb_status hb_index_push_kv(hb_index*, const uint8_t* key, size_t klen, const uint8_t* val, size_t vlen);
+
+/* Route (b): flat arrays (bench / tests).  ids ascending & unique; rows = n x dims f32 (float
+ * metrics) or n x ceil(dims/64) u64 code words (binary metrics); hdr = n header norms (Cosine,
+ * BQ-Cosine) or NULL; per layer l: offsets[l] has n+1 u64 entries, nbrs[l] holds neighbour ITEM IDS,
+ * ascending inside each list; entry_points are item ids in metadata order. */
+hb_status hb_index_from_arrays(hb_index*, uint32_t dims, const uint32_t* ids, uint64_t n, const void* rows,
+                               const float* hdr, uint32_t n_layers, const uint64_t* const* offsets,
+                               const uint32_t* const* nbrs, const uint32_t* entry_points, uint32_t n_ep,
+                               uint32_t max_level);
+
+/* Runs the Reader::open checks (MissingMetadata, UnmatchingDistance, NeedBuild), flattens the
+ * roaring edge lists into per-layer CSR over dense ranks, repacks rows into the 16-byte aligned
+ * device layout and uploads everything to `device`.  After this the index is immutable. */
+hb_status hb_index_finalize(hb_index*, int device);
+
+void hb_index_free(hb_index*);
+
+/* Reader accessors (src/reader.rs:545-573) */
+uint32_t hb_index_dimensions(const hb_index*);
+uint64_t hb_index_n_items(const hb_index*);
+uint32_t hb_index_n_entry_points(const hb_index*);
+uint32_t hb_index_max_level(const hb_index*);
+hb_status hb_index_version(const hb_index*, uint32_t* major, uint32_t* minor, uint32_t* patch);
+/* Reader::item_ids: copies min(cap, n) ascending ids */
+uint64_t hb_index_item_ids(const hb_index*, uint32_t* out, uint64_t cap);
+/* Reader::contains_item (reader.rs:595-601) */
+int hb_index_contains_item(const hb_index*, uint32_t item);
+/* Reader::item_vector (reader.rs:581-587): decoded f32 vector truncated to `dimensions`; HB_EINVAL if absent */
+hb_status hb_index_item_vector(const hb_index*, uint32_t item, float* out);
+
+/* ---- QueryBuilder (src/reader.rs:60-261) ------------------------------------------------------ */
+typedef struct {
+    const uint32_t* candidates; /* QueryBuilder::candidates (reader.rs:200-203): item ids, any order; NULL = none */
+    uint64_t n_candidates;
+    int has_candidates;         /* distinguishes "no bitmap" from "empty bitmap" */
+    uint32_t linear_below;      /* QueryBuilder::linear_below, default 1000 (reader.rs:29,234-237) */
+    float linear_below_ratio;   /* QueryBuilder::linear_below_ratio, default 1.0 (reader.rs:32,252-260) */
+} hb_query_opts;
+
+/* per-query counters written by the search kernels (u64 each) */
+enum { HB_CTR_DIST_UPPER = 0, HB_CTR_DIST_L0 = 1, HB_CTR_EXP_UPPER = 2, HB_CTR_EXP_L0 = 3,
+       HB_CTR_DEG_UPPER = 4, HB_CTR_DEG_L0 = 5, HB_CTR_FLAGS = 6, HB_CTR_RESERVED = 7, HB_N_CTR = 8 };
+enum { HB_FLAG_FALLBACK = 1, HB_FLAG_LINEAR = 2, HB_FLAG_SLOW_PATH = 4 };
+
+/* reader.nns(count).ef_search(..).by_vector(..) for a batch of nq queries (reader.rs:132-148 ->
+ * 642-665 -> 722-800).  `count` = nns(count); `ef` = the QueryBuilder.ef field as the reference
+ * holds it (100 by default, max(ef,count) after ef_search()).  q = nq x dims f32, row-major, host.
+ * out_ids/out_dist: nq x count; out_len: nq (number of valid results per query);
+ * out_counters: nq x HB_N_CTR u64 or NULL.  opts may be NULL.  Returns HB_EDIM if dims mismatch. */
+hb_status hb_search_by_vector(const hb_index*, const float* q, uint64_t nq, uint32_t dims, uint32_t count, uint32_t ef,
+                              const hb_query_opts* opts, uint32_t* out_ids, float* out_dist, uint32_t* out_len,
+                              uint64_t* out_counters);
+
+/* reader.nns(count).by_item(..) for a batch (reader.rs:81-89 -> 809-894).  out_len[i] = UINT32_MAX
+ * encodes `Ok(None)` (item absent / nothing to search). */
+hb_status hb_search_by_item(const hb_index*, const uint32_t* items, uint64_t nq, uint32_t count, uint32_t ef,
+                            const hb_query_opts* opts, uint32_t* out_ids, float* out_dist, uint32_t* out_len,
+                            uint64_t* out_counters);
+
+/* Same search with every buffer already resident on the index's device, enqueued on `stream`
+ * (a cudaStream_t) with no host synchronisation: used to time the kernels alone.  d_out_counters may be NULL. */
+hb_status hb_search_by_vector_device(const hb_index*, const float* d_q, uint64_t nq, uint32_t count, uint32_t ef,
+                                     uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len,
+                                     uint64_t* d_out_counters, void* stream);
+
+/* Exact k-NN in the index metric over all items (recall ground truth; the reference's analogue is
+ * brute_force_search over every id, reader.rs:668-711).  Ties broken by (distance bits, id). */
+hb_status hb_exact_knn(const hb_index*, const float* q, uint64_t nq, uint32_t dims, uint32_t k, uint32_t* out_ids, float* out_dist);
+
+/* Merge `n_parts` per-shard top-k lists (each nq x k, ids + distances, padded with id=UINT32_MAX)
+ * into the global top-k by (distance bits, id) — the step after the all-gather when an index is
+ * sharded by item id.  Buffers are DEVICE pointers laid out [part][nq][k]; runs on `stream`. */
+hb_status hb_merge_topk_device(int device, const uint32_t* d_ids, const float* d_dist, uint32_t n_parts, uint64_t nq,
+                               uint32_t k, uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len, void* stream);
+
+/* number of kernel launches issued by this library in this process (for bench gpu_launches) */
+uint64_t hb_launch_count(void);
+
+const char* hb_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
