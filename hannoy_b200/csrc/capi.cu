@@ -1,0 +1,554 @@
+// capi.cu — the C-ABI of libhannoy_b200.so (include/hannoy_b200.h): index lifecycle, upload, workspaces
+// and the host-facing search entry points.  No CPU compute path exists: without a device every compute
+// call fails with HB_ECUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.h"
+
+namespace hb {
+const char* last_error();
+}
+using namespace hb;
+
+#define CUDA_TRY(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            set_error("%s failed: %s", #expr, cudaGetErrorString(_e));                   \
+            return HB_ECUDA;                                                             \
+        }                                                                                \
+    } while (0)
+
+static const char* kMetricNames[] = {"euclidean", "cosine", "manhattan", "hamming", "binary quantized cosine",
+                                     "binary quantized euclidean", "binary quantized manhattan"};
+
+// device-side re-layout of natural rows into the search layout (see RowKind in common.h)
+__global__ void layout_rows_kernel(const uint8_t* __restrict__ nat, size_t nat_stride, uint8_t* __restrict__ out,
+                                   uint32_t out_stride, uint64_t n, uint32_t dims, int kind) {
+    uint64_t row = blockIdx.x;
+    if (row >= n) return;
+    const uint8_t* src = nat + row * nat_stride;
+    uint8_t* dst = out + row * (size_t)out_stride;
+    for (uint32_t i = threadIdx.x; i < out_stride / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(dst)[i] = 0;
+    __syncthreads();
+    if (kind == KIND_F32_WARP) {
+        uint32_t blocks = dims / 32, chunks = (blocks + 3) / 4, main = blocks * 32;
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+        uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+        for (uint32_t e = threadIdx.x; e < dims; e += blockDim.x) {
+            uint32_t v = s[e];
+            if (e < main) {
+                uint32_t blk = e >> 5, j = e & 31;
+                d[(blk >> 2) * 128 + j * 4 + (blk & 3)] = v;
+            } else {
+                d[chunks * 128 + (e - main)] = v;
+            }
+        }
+    } else {
+        for (size_t i = threadIdx.x; i < nat_stride / 4; i += blockDim.x)
+            reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+    }
+}
+
+extern "C" {
+
+const char* hb_metric_name(hb_metric m) { return ((int)m >= 0 && (int)m < 7) ? kMetricNames[(int)m] : "unknown"; }
+int hb_metric_from_name(const char* name) {
+    if (!name) return -1;
+    for (int i = 0; i < 7; ++i)
+        if (!std::strcmp(name, kMetricNames[i])) return i;
+    return -1;
+}
+const char* hb_last_error(void) { return last_error(); }
+uint64_t hb_launch_count(void) { return g_launches; }
+
+hb_status hb_index_begin(hb_metric m, uint16_t index, hb_index** out) {
+    if (!out || (int)m < 0 || (int)m > 6) { set_error("hb_index_begin: bad arguments"); return HB_EINVAL; }
+    hb_index* ix = new (std::nothrow) hb_index();
+    if (!ix) return HB_ENOMEM;
+    ix->metric = m;
+    ix->index = index;
+    *out = ix;
+    return HB_OK;
+}
+
+hb_status hb_index_push_kv(hb_index* ix, const uint8_t* key, size_t klen, const uint8_t* val, size_t vlen) {
+    if (!ix || !key || (!val && vlen)) { set_error("hb_index_push_kv: null argument"); return HB_EINVAL; }
+    if (ix->finalized) { set_error("index already finalized"); return HB_ESTATE; }
+    try {
+        return decode_kv(ix, key, klen, val, vlen);
+    } catch (const std::bad_alloc&) {
+        return HB_ENOMEM;
+    }
+}
+
+hb_status hb_index_from_arrays(hb_index* ix, uint32_t dims, const uint32_t* ids, uint64_t n, const void* rows,
+                               const float* hdr, uint32_t n_layers, const uint64_t* const* offsets,
+                               const uint32_t* const* nbrs, const uint32_t* entry_points, uint32_t n_ep,
+                               uint32_t max_level) {
+    if (!ix) return HB_EINVAL;
+    if (ix->finalized) { set_error("index already finalized"); return HB_ESTATE; }
+    if (n >= 0xffffffffull) { set_error("too many items"); return HB_EINVAL; }
+    if (n && (!ids || !rows)) { set_error("hb_index_from_arrays: null ids/rows"); return HB_EINVAL; }
+    if (n_layers > (uint32_t)MAX_LEVELS || (n && max_level >= n_layers)) { set_error("bad layer count"); return HB_EINVAL; }
+    try {
+        ix->dims = dims;
+        ix->ids.assign(ids, ids + n);
+        for (uint64_t i = 1; i < n; ++i)
+            if (ids[i] <= ids[i - 1]) { set_error("ids must be strictly ascending"); return HB_EINVAL; }
+        bool bin = ix->metric >= HB_HAMMING;
+        ix->host_row_bytes = bin ? 8 * (((size_t)dims + 63) / 64) : 4 * (size_t)dims;
+        ix->host_rows.assign((const uint8_t*)rows, (const uint8_t*)rows + n * ix->host_row_bytes);
+        if (hdr) ix->host_hdr.assign(hdr, hdr + n);
+        else ix->host_hdr.assign(n, 0.0f);
+        ix->layers.assign(n_layers, HostLayer());
+        for (uint32_t l = 0; l < n_layers; ++l) {
+            HostLayer& hl = ix->layers[l];
+            hl.off.assign(offsets[l], offsets[l] + n + 1);
+            uint64_t nnz = n ? hl.off[n] : 0;
+            hl.nbr.resize(nnz);
+            for (uint64_t e = 0; e < nnz; ++e) {
+                int64_t s = slot_of(ix, nbrs[l][e]);
+                if (s < 0) { set_error("layer %u: neighbour id %u is not an item", l, nbrs[l][e]); return HB_EFORMAT; }
+                hl.nbr[e] = (uint32_t)s;
+            }
+        }
+        ix->eps.clear();
+        for (uint32_t i = 0; i < n_ep; ++i) {
+            int64_t s = slot_of(ix, entry_points[i]);
+            if (s < 0) { set_error("entry point %u is not an item", entry_points[i]); return HB_EFORMAT; }
+            ix->eps.push_back((uint32_t)s);
+        }
+        ix->max_level = max_level;
+        ix->have_metadata = true;
+        ix->meta_distance = hb_metric_name(ix->metric);
+        ix->meta_dims = dims;
+        ix->version[0] = 0; ix->version[1] = 1; ix->version[2] = 3;
+    } catch (const std::bad_alloc&) {
+        return HB_ENOMEM;
+    }
+    return HB_OK;
+}
+
+}  // extern "C"
+
+template <class T>
+static hb_status upload(hb_index* ix, const T* host, size_t count, const T** out) {
+    void* d = nullptr;
+    size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+    CUDA_TRY(cudaMalloc(&d, bytes));
+    ix->dev_allocs.push_back(d);
+    if (count) CUDA_TRY(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T*)d;
+    return HB_OK;
+}
+
+extern "C" {
+
+hb_status hb_index_finalize(hb_index* ix, int device) {
+    if (!ix) return HB_EINVAL;
+    if (ix->finalized) { set_error("index already finalized"); return HB_ESTATE; }
+    hb_status st;
+    try {
+        if (!ix->kv_items.empty() || !ix->kv_links.empty() || ix->ids.empty()) {
+            // KV route (or an empty index): run the Reader::open checks and flatten
+            if (ix->ids.empty()) {
+                st = build_host_snapshot_from_kv(ix);
+                if (st != HB_OK) return st;
+            }
+        }
+    } catch (const std::bad_alloc&) {
+        return HB_ENOMEM;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device available (libhannoy_b200 has no CPU path)"); return HB_ECUDA; }
+    if (device < 0 || device >= ndev) { set_error("bad device %d", device); return HB_EINVAL; }
+    CUDA_TRY(cudaSetDevice(device));
+    ix->device = device;
+    DevIndex& d = ix->dev;
+    size_t n = ix->ids.size();
+    d.n = (uint32_t)n;
+    d.dims = ix->dims;
+    d.metric = (int)ix->metric;
+    d.kind = kind_for(ix->metric, ix->dims);
+    d.row_stride = device_row_stride(d.kind, ix->dims);
+    if (d.kind == KIND_F32_WARP) {
+        uint32_t blocks = ix->dims / 32;
+        d.n_chunks = (blocks + 3) / 4;
+        d.tail = ix->dims % 32;
+        d.tail_off = d.n_chunks * 128;
+    }
+    d.n_words = (ix->dims + 63) / 64;
+    d.max_level = ix->max_level;
+    d.n_layers = (uint32_t)ix->layers.size();
+    if (d.n_layers > (uint32_t)MAX_LEVELS) { set_error("too many layers"); return HB_EINVAL; }
+    if (n) {
+        // rows: upload natural encoding in slabs, re-layout on the device
+        void* drows = nullptr;
+        CUDA_TRY(cudaMalloc(&drows, std::max<size_t>(n * (size_t)d.row_stride, 16)));
+        ix->dev_allocs.push_back(drows);
+        const size_t slab_rows = std::max<size_t>(1, (256u << 20) / std::max<size_t>(ix->host_row_bytes, 1));
+        void* stage = nullptr;
+        CUDA_TRY(cudaMalloc(&stage, slab_rows * ix->host_row_bytes));
+        for (size_t r0 = 0; r0 < n; r0 += slab_rows) {
+            size_t nr = std::min(slab_rows, n - r0);
+            CUDA_TRY(cudaMemcpy(stage, ix->host_rows.data() + r0 * ix->host_row_bytes, nr * ix->host_row_bytes, cudaMemcpyHostToDevice));
+            layout_rows_kernel<<<(unsigned)nr, 128>>>((const uint8_t*)stage, ix->host_row_bytes,
+                                                      (uint8_t*)drows + r0 * (size_t)d.row_stride, d.row_stride, nr, ix->dims, d.kind);
+            ++g_launches;
+            CUDA_TRY(cudaDeviceSynchronize());
+        }
+        cudaFree(stage);
+        d.rows = (const uint8_t*)drows;
+    }
+    if ((st = upload(ix, ix->host_hdr.data(), n, &d.hdr)) != HB_OK) return st;
+    if ((st = upload(ix, ix->ids.data(), n, &d.ids)) != HB_OK) return st;
+    for (uint32_t l = 0; l < d.n_layers; ++l) {
+        HostLayer& hl = ix->layers[l];
+        if (hl.off.size() != n + 1) hl.off.assign(n + 1, 0);
+        if (hl.off[n] >= 0xffffffffull) { set_error("layer %u has too many edges for 32-bit offsets", l); return HB_EINVAL; }
+        std::vector<uint32_t> off32(hl.off.begin(), hl.off.end());
+        if ((st = upload(ix, off32.data(), off32.size(), &d.off[l])) != HB_OK) return st;
+        if ((st = upload(ix, hl.nbr.data(), hl.nbr.size(), &d.nbr[l])) != HB_OK) return st;
+    }
+    if ((st = upload(ix, ix->eps.data(), ix->eps.size(), &d.eps)) != HB_OK) return st;
+    d.n_ep = (uint32_t)ix->eps.size();
+    ix->finalized = true;
+    return HB_OK;
+}
+
+static void free_workspace(Workspace* w) {
+    if (!w) return;
+    cudaFree(w->visited); cudaFree(w->touched); cudaFree(w->work_counter); cudaFree(w->overflow_list);
+    cudaFree(w->n_overflow); cudaFree(w->gheap); cudaFree(w->d_q); cudaFree(w->d_out); cudaFree(w->d_cand);
+    if (w->stream) cudaStreamDestroy((cudaStream_t)w->stream);
+    delete w;
+}
+
+void hb_index_free(hb_index* ix) {
+    if (!ix) return;
+    if (ix->device >= 0) cudaSetDevice(ix->device);
+    for (Workspace* w : ix->ws_all) free_workspace(w);
+    for (void* p : ix->dev_allocs) cudaFree(p);
+    delete ix;
+}
+
+uint32_t hb_index_dimensions(const hb_index* ix) { return ix ? ix->dims : 0; }
+uint64_t hb_index_n_items(const hb_index* ix) { return ix ? ix->ids.size() : 0; }
+uint32_t hb_index_n_entry_points(const hb_index* ix) { return ix ? (uint32_t)ix->eps.size() : 0; }
+uint32_t hb_index_max_level(const hb_index* ix) { return ix ? ix->max_level : 0; }
+hb_status hb_index_version(const hb_index* ix, uint32_t* major, uint32_t* minor, uint32_t* patch) {
+    if (!ix) return HB_EINVAL;
+    if (major) *major = ix->version[0];
+    if (minor) *minor = ix->version[1];
+    if (patch) *patch = ix->version[2];
+    return HB_OK;
+}
+uint64_t hb_index_item_ids(const hb_index* ix, uint32_t* out, uint64_t cap) {
+    if (!ix) return 0;
+    uint64_t m = std::min<uint64_t>(cap, ix->ids.size());
+    if (out) std::copy(ix->ids.begin(), ix->ids.begin() + m, out);
+    return ix->ids.size();
+}
+int hb_index_contains_item(const hb_index* ix, uint32_t item) { return ix && slot_of(ix, item) >= 0; }
+hb_status hb_index_item_vector(const hb_index* ix, uint32_t item, float* out) {
+    if (!ix || !out) return HB_EINVAL;
+    int64_t s = slot_of(ix, item);
+    if (s < 0) { set_error("item %u not found", item); return HB_EINVAL; }
+    const uint8_t* row = ix->host_rows.data() + (size_t)s * ix->host_row_bytes;
+    if (ix->metric >= HB_HAMMING) {
+        // Binary::to_vec gives 0.0 / 1.0, BinaryQuantized::to_vec gives -1.0 / 1.0 (unaligned_vector/binary*.rs)
+        for (uint32_t e = 0; e < ix->dims; ++e) {
+            uint64_t w;
+            std::memcpy(&w, row + 8 * (e / 64), 8);
+            bool bit = (w >> (e % 64)) & 1;
+            out[e] = ix->metric == HB_HAMMING ? (bit ? 1.0f : 0.0f) : (bit ? 1.0f : -1.0f);
+        }
+    } else {
+        std::memcpy(out, row, 4 * (size_t)ix->dims);
+    }
+    return HB_OK;
+}
+
+}  // extern "C"
+
+// ---- workspaces ---------------------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return v ? std::atoi(v) : dflt;
+}
+
+static hb_status make_workspace(hb_index* ix, Workspace** out) {
+    Workspace* w = new Workspace();
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, ix->device));
+    int bps = std::max(1, std::min(16, env_int("HB_BLOCKS_PER_SM", 4)));
+    w->n_slots = prop.multiProcessorCount * bps * SEARCH_WARPS_PER_BLOCK;
+    size_t n = ix->ids.size();
+    w->vis_words = (uint32_t)(((n + 31) / 32 + 31) / 32 * 32);
+    if (w->vis_words == 0) w->vis_words = 32;
+    w->touched_cap = (uint32_t)std::max(1024, env_int("HB_TOUCHED_CAP", 16384));
+    CUDA_TRY(cudaMalloc(&w->visited, (size_t)w->n_slots * w->vis_words * 4));
+    CUDA_TRY(cudaMemset(w->visited, 0, (size_t)w->n_slots * w->vis_words * 4));
+    CUDA_TRY(cudaMalloc(&w->touched, (size_t)w->n_slots * w->touched_cap * 4));
+    CUDA_TRY(cudaMalloc(&w->work_counter, 16));
+    CUDA_TRY(cudaMalloc(&w->n_overflow, 16));
+    CUDA_TRY(cudaMemset(w->n_overflow, 0, 16));
+    w->gheap_entries_per_slot = 2 * (uint64_t)(n + ix->eps.size() + 64);
+    uint64_t per_slot = w->gheap_entries_per_slot * 8;
+    int slow = (int)std::min<uint64_t>(64, std::max<uint64_t>(4, (512ull << 20) / per_slot));
+    slow = slow / SEARCH_WARPS_PER_BLOCK * SEARCH_WARPS_PER_BLOCK;
+    w->slow_slots = std::min(slow, w->n_slots);
+    CUDA_TRY(cudaMalloc(&w->gheap, (size_t)w->slow_slots * per_slot));
+    cudaStream_t s;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    w->stream = s;
+    *out = w;
+    return HB_OK;
+}
+
+static hb_status acquire_ws(const hb_index* cix, Workspace** out) {
+    hb_index* ix = const_cast<hb_index*>(cix);
+    {
+        std::lock_guard<std::mutex> g(ix->ws_mu);
+        if (!ix->ws_free.empty()) { *out = ix->ws_free.back(); ix->ws_free.pop_back(); return HB_OK; }
+    }
+    Workspace* w = nullptr;
+    hb_status st = make_workspace(ix, &w);
+    if (st != HB_OK) { free_workspace(w); return st; }
+    std::lock_guard<std::mutex> g(ix->ws_mu);
+    ix->ws_all.push_back(w);
+    *out = w;
+    return HB_OK;
+}
+static void release_ws(const hb_index* cix, Workspace* w) {
+    hb_index* ix = const_cast<hb_index*>(cix);
+    std::lock_guard<std::mutex> g(ix->ws_mu);
+    ix->ws_free.push_back(w);
+}
+static hb_status grow(void** p, size_t* have, size_t need) {
+    if (*have >= need) return HB_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *have = 0;
+    CUDA_TRY(cudaMalloc(p, need));
+    *have = need;
+    return HB_OK;
+}
+
+// Fill the two passes' parameters and launch.  `ov_cap` entries must be available in w->overflow_list.
+static hb_status run_search(const hb_index* ix, Workspace* w, SearchParams base, void* stream) {
+    const DevIndex& d = ix->dev;
+    uint64_t nq = base.nq;
+    if (nq > 0xfffffff0ull) { set_error("batch too large"); return HB_EINVAL; }
+    if (w->overflow_cap < nq) {
+        if (w->overflow_list) cudaFree(w->overflow_list);
+        w->overflow_list = nullptr; w->overflow_cap = 0;
+        CUDA_TRY(cudaMalloc(&w->overflow_list, std::max<uint64_t>(nq, 1024) * 4));
+        w->overflow_cap = std::max<uint64_t>(nq, 1024);
+    }
+    base.ix = d;
+    base.visited = w->visited; base.vis_words = w->vis_words;
+    base.touched = w->touched; base.touched_cap = w->touched_cap;
+    base.work_counter = w->work_counter;
+    base.overflow_list = w->overflow_list; base.n_overflow = w->n_overflow;
+    base.n_work = (uint32_t)nq;
+    base.q_smem_bytes = (d.row_stride + 15) & ~15u;
+    const uint32_t ef0 = std::max(base.ef_raw, base.count);
+    SearchParams fast = base, slow = base;
+    if (base.mode >= 2) {
+        fast.res_cap = (base.count + 32 + 31) & ~31u;
+        fast.q_cap = 0;
+    } else {
+        fast.res_cap = (std::max(ef0, d.n_ep) + 32 + 31) & ~31u;
+        fast.q_cap = (std::max(2 * ef0, d.n_ep) + 64 + 31) & ~31u;
+    }
+    fast.pass = 0;
+    size_t per_block = search_smem_per_warp(fast) * SEARCH_WARPS_PER_BLOCK;
+    int blocks_fast = w->n_slots / SEARCH_WARPS_PER_BLOCK;
+    if (per_block > (size_t)SEARCH_MAX_SMEM) {
+        fast.res_cap = 0; fast.q_cap = 0;  // every query takes the global-memory pass
+    }
+    slow.pass = 1;
+    slow.gheap = (unsigned long long*)w->gheap;
+    uint64_t half = w->gheap_entries_per_slot / 2;
+    slow.res_cap = (uint32_t)half; slow.q_cap = (uint32_t)half;
+    if ((size_t)slow.q_smem_bytes * SEARCH_WARPS_PER_BLOCK > (size_t)SEARCH_MAX_SMEM) { set_error("dimension too large"); return HB_EINVAL; }
+    int blocks_slow = w->slow_slots / SEARCH_WARPS_PER_BLOCK;
+    return launch_search(fast, slow, blocks_fast, blocks_slow, stream);
+}
+
+struct CandInfo {
+    std::vector<uint32_t> slots;  // candidates ∩ items, ascending slots
+    std::vector<uint32_t> bits;
+};
+
+static bool should_linear_scan(size_t n_items, size_t cand_in_db, const hb_query_opts* o) {  // reader.rs:622-640
+    if (n_items == 0 || !o || !o->has_candidates) return false;
+    bool below_threshold = (uint64_t)cand_in_db < (uint64_t)o->linear_below;
+    bool below_ratio = ((float)cand_in_db / (float)n_items) <= o->linear_below_ratio;
+    return below_threshold && below_ratio;
+}
+
+static hb_status search_host(const hb_index* ix, const float* q, const uint32_t* items, uint64_t nq, uint32_t count, uint32_t ef,
+                             const hb_query_opts* opts, uint32_t* out_ids, float* out_dist, uint32_t* out_len, uint64_t* out_ctr) {
+    const bool by_item = items != nullptr;
+    const size_t n = ix->ids.size();
+    if (nq == 0) return HB_OK;
+    if (!out_len || (count && (!out_ids || !out_dist))) { set_error("null output buffer"); return HB_EINVAL; }
+    auto none = [&](uint32_t v) {
+        for (uint64_t i = 0; i < nq; ++i) out_len[i] = v;
+        if (out_ctr) std::memset(out_ctr, 0, nq * HB_N_CTR * 8);
+    };
+    // reader.rs:654-656 / 822-824
+    CandInfo ci;
+    bool has_cand = opts && opts->has_candidates;
+    if (has_cand) {
+        std::vector<uint32_t> c(opts->candidates, opts->candidates + opts->n_candidates);
+        std::sort(c.begin(), c.end());
+        c.erase(std::unique(c.begin(), c.end()), c.end());
+        for (uint32_t id : c) { int64_t s = slot_of(ix, id); if (s >= 0) ci.slots.push_back((uint32_t)s); }
+    }
+    if (n == 0 || (has_cand && ci.slots.empty())) { none(by_item ? 0xffffffffu : 0u); return HB_OK; }
+    bool linear = has_cand && should_linear_scan(n, ci.slots.size(), opts);
+    if (count == 0 && !by_item) { none(0); return HB_OK; }
+
+    CUDA_TRY(cudaSetDevice(ix->device));
+    Workspace* w = nullptr;
+    hb_status st = acquire_ws(ix, &w);
+    if (st != HB_OK) return st;
+    cudaStream_t stream = (cudaStream_t)w->stream;
+    auto fail = [&](hb_status s) { release_ws(ix, w); return s; };
+
+    size_t q_bytes = by_item ? nq * 4 : nq * (size_t)ix->dims * 4;
+    if ((st = grow(&w->d_q, &w->d_q_bytes, q_bytes)) != HB_OK) return fail(st);
+    size_t ids_b = nq * (size_t)count * 4, len_b = nq * 4, ctr_b = out_ctr ? nq * HB_N_CTR * 8 : 0;
+    size_t off_dist = (ids_b + 255) & ~(size_t)255, off_len = (off_dist + ids_b + 255) & ~(size_t)255;
+    size_t off_ctr = (off_len + len_b + 255) & ~(size_t)255;
+    if ((st = grow(&w->d_out, &w->d_out_bytes, off_ctr + ctr_b + 256)) != HB_OK) return fail(st);
+    std::vector<uint32_t> qslots;
+    if (by_item) {
+        qslots.resize(nq);
+        for (uint64_t i = 0; i < nq; ++i) { int64_t s = slot_of(ix, items[i]); qslots[i] = s < 0 ? 0xffffffffu : (uint32_t)s; }
+        if (cudaMemcpyAsync(w->d_q, qslots.data(), q_bytes, cudaMemcpyHostToDevice, stream) != cudaSuccess) { set_error("H2D failed"); return fail(HB_ECUDA); }
+    } else {
+        if (cudaMemcpyAsync(w->d_q, q, q_bytes, cudaMemcpyHostToDevice, stream) != cudaSuccess) { set_error("H2D failed"); return fail(HB_ECUDA); }
+    }
+    SearchParams p;
+    if (has_cand) {
+        size_t words = (n + 31) / 32;
+        ci.bits.assign(words, 0);
+        for (uint32_t s : ci.slots) ci.bits[s >> 5] |= 1u << (s & 31);
+        size_t cb = words * 4, off_slots = (cb + 255) & ~(size_t)255;
+        if ((st = grow(&w->d_cand, &w->d_cand_bytes, off_slots + ci.slots.size() * 4 + 256)) != HB_OK) return fail(st);
+        cudaMemcpyAsync(w->d_cand, ci.bits.data(), cb, cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync((uint8_t*)w->d_cand + off_slots, ci.slots.data(), ci.slots.size() * 4, cudaMemcpyHostToDevice, stream);
+        p.cand_bits = (const uint32_t*)w->d_cand;
+        p.cand_slots = (const uint32_t*)((uint8_t*)w->d_cand + off_slots);
+        p.n_cand_slots = (uint32_t)ci.slots.size();
+    }
+    p.q = by_item ? nullptr : (const float*)w->d_q;
+    p.q_slots = by_item ? (const uint32_t*)w->d_q : nullptr;
+    p.nq = nq; p.count = count; p.ef_raw = ef;
+    p.mode = (by_item ? 1 : 0) | (linear ? 2 : 0);
+    uint8_t* ob = (uint8_t*)w->d_out;
+    p.out_ids = (uint32_t*)ob; p.out_dist = (float*)(ob + off_dist); p.out_len = (uint32_t*)(ob + off_len);
+    p.out_ctr = out_ctr ? (uint64_t*)(ob + off_ctr) : nullptr;
+    if ((st = run_search(ix, w, p, stream)) != HB_OK) return fail(st);
+    if (ids_b) {
+        cudaMemcpyAsync(out_ids, p.out_ids, ids_b, cudaMemcpyDeviceToHost, stream);
+        cudaMemcpyAsync(out_dist, p.out_dist, ids_b, cudaMemcpyDeviceToHost, stream);
+    }
+    cudaMemcpyAsync(out_len, p.out_len, len_b, cudaMemcpyDeviceToHost, stream);
+    if (out_ctr) cudaMemcpyAsync(out_ctr, p.out_ctr, ctr_b, cudaMemcpyDeviceToHost, stream);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { set_error("search failed: %s", cudaGetErrorString(e)); return fail(HB_ECUDA); }
+    release_ws(ix, w);
+    return HB_OK;
+}
+
+extern "C" {
+
+hb_status hb_search_by_vector(const hb_index* ix, const float* q, uint64_t nq, uint32_t dims, uint32_t count, uint32_t ef,
+                              const hb_query_opts* opts, uint32_t* out_ids, float* out_dist, uint32_t* out_len,
+                              uint64_t* out_counters) {
+    if (!ix || (!q && nq)) { set_error("hb_search_by_vector: null argument"); return HB_EINVAL; }
+    if (!ix->finalized) { set_error("index not finalized"); return HB_ESTATE; }
+    if (dims != ix->dims) {  // Error::InvalidVecDimension — reader.rs:133-138
+        set_error("Invalid vector dimensions. Got %u but expected %u", dims, ix->dims);
+        return HB_EDIM;
+    }
+    try {
+        return search_host(ix, q, nullptr, nq, count, ef, opts, out_ids, out_dist, out_len, out_counters);
+    } catch (const std::bad_alloc&) {
+        return HB_ENOMEM;
+    }
+}
+
+hb_status hb_search_by_item(const hb_index* ix, const uint32_t* items, uint64_t nq, uint32_t count, uint32_t ef,
+                            const hb_query_opts* opts, uint32_t* out_ids, float* out_dist, uint32_t* out_len,
+                            uint64_t* out_counters) {
+    if (!ix || (!items && nq)) { set_error("hb_search_by_item: null argument"); return HB_EINVAL; }
+    if (!ix->finalized) { set_error("index not finalized"); return HB_ESTATE; }
+    try {
+        return search_host(ix, nullptr, items, nq, count, ef, opts, out_ids, out_dist, out_len, out_counters);
+    } catch (const std::bad_alloc&) {
+        return HB_ENOMEM;
+    }
+}
+
+hb_status hb_search_by_vector_device(const hb_index* ix, const float* d_q, uint64_t nq, uint32_t count, uint32_t ef,
+                                     uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len,
+                                     uint64_t* d_out_counters, void* stream) {
+    if (!ix || !d_q || !d_out_ids || !d_out_dist || !d_out_len) { set_error("null argument"); return HB_EINVAL; }
+    if (!ix->finalized) { set_error("index not finalized"); return HB_ESTATE; }
+    if (ix->ids.empty() || nq == 0 || count == 0) {
+        if (nq) cudaMemsetAsync(d_out_len, 0, nq * 4, (cudaStream_t)stream);
+        return HB_OK;
+    }
+    CUDA_TRY(cudaSetDevice(ix->device));
+    Workspace* w = nullptr;
+    hb_status st = acquire_ws(ix, &w);
+    if (st != HB_OK) return st;
+    SearchParams p;
+    p.q = d_q; p.nq = nq; p.count = count; p.ef_raw = ef; p.mode = 0;
+    p.out_ids = d_out_ids; p.out_dist = d_out_dist; p.out_len = d_out_len; p.out_ctr = d_out_counters;
+    st = run_search(ix, w, p, stream);
+    // the workspace is only reusable once the stream has drained; the caller serialises calls on `stream`
+    release_ws(ix, w);
+    return st;
+}
+
+hb_status hb_exact_knn(const hb_index* ix, const float* q, uint64_t nq, uint32_t dims, uint32_t k, uint32_t* out_ids, float* out_dist) {
+    if (!ix || (!q && nq) || !out_ids || !out_dist) { set_error("null argument"); return HB_EINVAL; }
+    if (!ix->finalized) { set_error("index not finalized"); return HB_ESTATE; }
+    if (dims != ix->dims) { set_error("Invalid vector dimensions. Got %u but expected %u", dims, ix->dims); return HB_EDIM; }
+    if (nq == 0 || k == 0) return HB_OK;
+    CUDA_TRY(cudaSetDevice(ix->device));
+    float* dq = nullptr; uint32_t* dids = nullptr; float* dd = nullptr;
+    CUDA_TRY(cudaMalloc(&dq, nq * (size_t)dims * 4));
+    CUDA_TRY(cudaMalloc(&dids, nq * (size_t)k * 4));
+    CUDA_TRY(cudaMalloc(&dd, nq * (size_t)k * 4));
+    hb_status st = HB_OK;
+    if (cudaMemcpy(dq, q, nq * (size_t)dims * 4, cudaMemcpyHostToDevice) != cudaSuccess) st = HB_ECUDA;
+    if (st == HB_OK) st = launch_exact_knn(ix->dev, dq, nq, k, dids, dd, nullptr);
+    if (st == HB_OK && cudaDeviceSynchronize() != cudaSuccess) { set_error("exact_knn kernel failed: %s", cudaGetErrorString(cudaGetLastError())); st = HB_ECUDA; }
+    if (st == HB_OK) {
+        cudaMemcpy(out_ids, dids, nq * (size_t)k * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(out_dist, dd, nq * (size_t)k * 4, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(dq); cudaFree(dids); cudaFree(dd);
+    return st;
+}
+
+hb_status hb_merge_topk_device(int device, const uint32_t* d_ids, const float* d_dist, uint32_t n_parts, uint64_t nq,
+                               uint32_t k, uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len, void* stream) {
+    if (!d_ids || !d_dist || !d_out_ids || !d_out_dist) { set_error("null argument"); return HB_EINVAL; }
+    CUDA_TRY(cudaSetDevice(device));
+    return launch_merge_topk(d_ids, d_dist, n_parts, nq, k, d_out_ids, d_out_dist, d_out_len, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,165 @@
+// common.h — structures shared by the host side (snapshot.cpp, capi.cu) and the kernels.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/hannoy_b200.h"
+
+namespace hb {
+
+// How a row is laid out in HBM and which distance routine walks it.
+enum RowKind : int {
+    // f32, dims >= 32, Euclidean / Cosine.  Reproduces the AVX+FMA summation order of
+    // src/spaces/simple_avx.rs:17-110 with one warp per row: the row is stored in 128-float chunks,
+    // permuted so that lane j's float4 of chunk c holds elements {128c + 32t + j | t = 0..3};
+    // the n % 32 tail follows in natural order.
+    KIND_F32_WARP = 0,
+    // f32 in natural order, one lane per row, sequential arithmetic: Euclidean / Cosine with
+    // dims < 32 (SSE path simple_sse.rs:18-110 for 16..31, scalar simple.rs:49-51,81-83 below) and
+    // Manhattan at any dims (manhattan.rs:41-43 is a strictly sequential sum).
+    KIND_F32_LANE = 1,
+    // packed u64 words (Binary / BinaryQuantized codecs), popcount distances.
+    KIND_BIN = 2,
+};
+
+constexpr int MAX_LEVELS = 64;  // max_level is a u8 in the metadata; P(level >= 16) < 1e-19 for M >= 4
+
+// Device view of one snapshotted index.  All pointers are device pointers.
+struct DevIndex {
+    uint32_t n = 0;        // number of items; slots are dense ranks 0..n-1 in ascending ItemId order
+    uint32_t dims = 0;
+    int metric = 0;
+    int kind = 0;
+    uint32_t row_stride = 0;  // bytes between rows (multiple of 16)
+    uint32_t n_chunks = 0;    // KIND_F32_WARP: 128-float chunks in the main part
+    uint32_t tail = 0;        // KIND_F32_WARP: dims % 32
+    uint32_t tail_off = 0;    // KIND_F32_WARP: float offset of the tail inside a row
+    uint32_t n_words = 0;     // KIND_BIN: u64 words per row = ceil(dims/64)
+    const uint8_t* rows = nullptr;
+    const float* hdr = nullptr;      // per-slot norm (Cosine, BQ-Cosine) or nullptr
+    const uint32_t* ids = nullptr;   // slot -> ItemId
+    uint32_t n_layers = 0;
+    uint32_t max_level = 0;
+    const uint32_t* off[MAX_LEVELS] = {};  // per layer: n+1 CSR offsets (u32; nnz < 2^32 checked at finalize)
+    const uint32_t* nbr[MAX_LEVELS] = {};  // per layer: neighbour SLOTS, ascending in each list
+    const uint32_t* eps = nullptr;         // entry point slots, metadata order
+    uint32_t n_ep = 0;
+};
+
+// One search call.
+struct SearchParams {
+    DevIndex ix;
+    const float* q = nullptr;          // nq x dims raw f32 queries (by_vector)
+    const uint32_t* q_slots = nullptr; // by_item: slot per query, UINT32_MAX = absent
+    uint64_t nq = 0;
+    uint32_t count = 0, ef_raw = 0;
+    int mode = 0;  // 0 by_vector (hnsw), 1 by_item (hnsw), 2 by_vector linear scan, 3 by_item linear scan
+    const uint32_t* cand_slots = nullptr;  // linear scan: candidate slots, ascending
+    uint32_t n_cand_slots = 0;
+    const uint32_t* cand_bits = nullptr;  // dense candidates bitset over slots, or nullptr
+    uint32_t* out_ids = nullptr;
+    float* out_dist = nullptr;
+    uint32_t* out_len = nullptr;
+    uint64_t* out_ctr = nullptr;  // nq x HB_N_CTR or nullptr
+    // workspace
+    uint32_t* visited = nullptr;       // n_slots x vis_words
+    uint32_t vis_words = 0;
+    uint32_t* touched = nullptr;       // n_slots x touched_cap
+    uint32_t touched_cap = 0;
+    unsigned long long* work_counter = nullptr;  // [2]: one per pass
+    uint32_t* overflow_list = nullptr; // queries that need the slow path
+    uint32_t* n_overflow = nullptr;
+    uint32_t res_cap = 0, q_cap = 0;   // heap capacities (entries) for this pass
+    unsigned long long* gheap = nullptr;  // slow pass: n_slots x (res_cap + q_cap) u64 in global memory
+    int pass = 0;                      // 0 = shared-memory heaps, 1 = global-memory heaps over overflow_list
+    uint32_t n_work = 0;               // pass 0: nq ; pass 1: read from *n_overflow on device
+    uint32_t q_smem_bytes = 0;         // per-warp query staging bytes
+};
+
+// ---- host-side snapshot -----------------------------------------------------------------------
+struct HostLayer {
+    std::vector<uint64_t> off;  // n+1
+    std::vector<uint32_t> nbr;  // slots
+};
+
+struct Workspace {
+    int n_slots = 0;
+    uint32_t* visited = nullptr;
+    uint32_t vis_words = 0;
+    uint32_t* touched = nullptr;
+    uint32_t touched_cap = 0;
+    unsigned long long* work_counter = nullptr;
+    uint32_t* overflow_list = nullptr;
+    uint64_t overflow_cap = 0;
+    uint32_t* n_overflow = nullptr;
+    uint64_t* gheap = nullptr;
+    uint64_t gheap_entries_per_slot = 0;
+    int slow_slots = 0;
+    void* stream = nullptr;  // cudaStream_t owned by the workspace (host API)
+    // staging buffers for the host API (grown on demand)
+    void* d_q = nullptr; size_t d_q_bytes = 0;
+    void* d_out = nullptr; size_t d_out_bytes = 0;
+    void* d_cand = nullptr; size_t d_cand_bytes = 0;
+};
+
+}  // namespace hb
+
+struct hb_index {
+    hb_metric metric = HB_EUCLIDEAN;
+    uint16_t index = 0;
+    bool finalized = false;
+    int device = -1;
+    // --- staging from push_kv ---
+    bool have_metadata = false;
+    std::string meta_distance;
+    uint32_t meta_dims = 0;
+    std::vector<uint32_t> meta_items;
+    std::vector<uint32_t> meta_eps;
+    uint32_t meta_max_level = 0;
+    uint32_t version[3] = {0, 0, 0};
+    bool need_build = false;
+    std::map<uint32_t, std::vector<uint8_t>> kv_items;                    // id -> header||vector bytes
+    std::map<std::pair<uint32_t, uint32_t>, std::vector<uint32_t>> kv_links;  // (id, layer) -> ids
+    // --- canonical host snapshot ---
+    uint32_t dims = 0;
+    std::vector<uint32_t> ids;      // ascending
+    size_t host_row_bytes = 0;      // natural encoding: 4*dims or 8*ceil(dims/64)
+    std::vector<uint8_t> host_rows; // natural order (for item_vector and re-layout)
+    std::vector<float> host_hdr;
+    std::vector<hb::HostLayer> layers;
+    std::vector<uint32_t> eps;      // slots
+    uint32_t max_level = 0;
+    // --- device ---
+    hb::DevIndex dev;
+    std::vector<void*> dev_allocs;
+    std::mutex ws_mu;
+    std::vector<hb::Workspace*> ws_free;
+    std::vector<hb::Workspace*> ws_all;
+};
+
+namespace hb {
+void set_error(const char* fmt, ...);
+// snapshot.cpp
+hb_status decode_kv(hb_index* ix, const uint8_t* key, size_t klen, const uint8_t* val, size_t vlen);
+hb_status build_host_snapshot_from_kv(hb_index* ix);
+bool roaring_decode(const uint8_t* p, size_t len, std::vector<uint32_t>& out);
+int64_t slot_of(const hb_index* ix, uint32_t id);
+// device row layout
+uint32_t device_row_stride(int kind, uint32_t dims);
+void layout_row(int kind, uint32_t dims, const uint8_t* natural, uint8_t* out);
+int kind_for(hb_metric m, uint32_t dims);
+// search.cu
+constexpr int SEARCH_WARPS_PER_BLOCK = 4;
+constexpr int SEARCH_MAX_SMEM = 200 * 1024;
+hb_status launch_search(const SearchParams& fast, const SearchParams& slow, int blocks_fast, int blocks_slow, void* stream);
+size_t search_smem_per_warp(const SearchParams& p);
+// exact.cu
+hb_status launch_exact_knn(const DevIndex& ix, const float* d_q, uint64_t nq, uint32_t k, uint32_t* d_ids, float* d_dist, void* stream);
+hb_status launch_merge_topk(const uint32_t* d_ids, const float* d_dist, uint32_t n_parts, uint64_t nq, uint32_t k,
+                            uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len, void* stream);
+extern unsigned long long g_launches;
+}  // namespace hb

@@ -1,0 +1,252 @@
+// snapshot.cpp — host side of Reader::open: decode the reference's LMDB key/value encoding, flatten the
+// roaring edge lists into CSR over dense ranks, and lay rows out for the device.
+// Product code: shares nothing with oracle/ (which has its own, independent, encoder+decoder).
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.h"
+
+namespace hb {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+static inline uint16_t le16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+static inline uint32_t le32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+static inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3]; }
+
+// Roaring "portable" serialization (RoaringFormatSpec), what roaring 0.10 writes for
+// RoaringBitmap::serialize_into and accepts in deserialize_from (src/roaring.rs:20,29; src/node.rs:143,164;
+// src/metadata.rs:40,58).  Containers: array (<= 4096 sorted u16), bitmap (1024 x u64), run (with cookie 12347).
+bool roaring_decode(const uint8_t* p, size_t len, std::vector<uint32_t>& out) {
+    const uint32_t SERIAL_COOKIE_NO_RUN = 12346, SERIAL_COOKIE = 12347, NO_OFFSET_THRESHOLD = 4;
+    if (len < 4) return false;
+    uint32_t cookie = le32(p);
+    size_t pos = 4, n = 0;
+    const uint8_t* run_bitmap = nullptr;
+    if ((cookie & 0xffff) == SERIAL_COOKIE) {
+        n = (size_t)(cookie >> 16) + 1;
+        size_t rb = (n + 7) / 8;
+        if (len < pos + rb) return false;
+        run_bitmap = p + pos;
+        pos += rb;
+    } else if (cookie == SERIAL_COOKIE_NO_RUN) {
+        if (len < 8) return false;
+        n = le32(p + 4);
+        pos = 8;
+    } else {
+        return false;
+    }
+    if (n > 65536 || len < pos + 4 * n) return false;
+    const uint8_t* desc = p + pos;
+    pos += 4 * n;
+    if (!run_bitmap || n >= NO_OFFSET_THRESHOLD) {
+        if (len < pos + 4 * n) return false;
+        pos += 4 * n;  // offset header (containers are read sequentially)
+    }
+    for (size_t i = 0; i < n; ++i) {
+        uint32_t hi = (uint32_t)le16(desc + 4 * i) << 16;
+        uint32_t card = (uint32_t)le16(desc + 4 * i + 2) + 1;
+        bool is_run = run_bitmap && ((run_bitmap[i >> 3] >> (i & 7)) & 1);
+        if (is_run) {
+            if (len < pos + 2) return false;
+            size_t n_runs = le16(p + pos);
+            pos += 2;
+            if (len < pos + 4 * n_runs) return false;
+            for (size_t r = 0; r < n_runs; ++r) {
+                uint32_t start = le16(p + pos), span = le16(p + pos + 2);
+                pos += 4;
+                if (start + span > 0xffff) return false;
+                for (uint32_t v = start; v <= start + span; ++v) out.push_back(hi | v);
+            }
+        } else if (card > 4096) {
+            if (len < pos + 8192) return false;
+            for (uint32_t w = 0; w < 1024; ++w) {
+                uint64_t x;
+                std::memcpy(&x, p + pos + 8 * w, 8);  // little-endian host
+                while (x) {
+                    out.push_back(hi | (w * 64 + (uint32_t)__builtin_ctzll(x)));
+                    x &= x - 1;
+                }
+            }
+            pos += 8192;
+        } else {
+            if (len < pos + 2 * (size_t)card) return false;
+            for (uint32_t k = 0; k < card; ++k) out.push_back(hi | le16(p + pos + 2 * k));
+            pos += 2 * (size_t)card;
+        }
+    }
+    return true;
+}
+
+static size_t header_size(hb_metric m) { return m == HB_HAMMING ? 8 : 4; }  // NodeHeaderHamming{idx: usize}
+
+// One raw LMDB pair.  Key = [index u16 BE][mode u8][item u32 BE][layer u8] (src/key.rs:54-82);
+// modes Metadata=0 Updated=1 Links=2 Item=3 (src/node_id.rs:11-21).
+hb_status decode_kv(hb_index* ix, const uint8_t* key, size_t klen, const uint8_t* val, size_t vlen) {
+    if (klen != 8) { set_error("key must be 8 bytes, got %zu", klen); return HB_EFORMAT; }
+    uint16_t index = (uint16_t)((key[0] << 8) | key[1]);
+    if (index != ix->index) return HB_OK;  // another index living in the same database
+    uint8_t mode = key[2];
+    uint32_t item = be32(key + 3);
+    uint8_t layer = key[7];
+    switch (mode) {
+        case 0: {
+            if (item == 0) {  // MetadataCodec — src/metadata.rs:49-73
+                const void* nul = std::memchr(val, 0, vlen);
+                if (!nul) { set_error("metadata: distance name not NUL-terminated"); return HB_EFORMAT; }
+                size_t nl = (const uint8_t*)nul - val;
+                ix->meta_distance.assign((const char*)val, nl);
+                const uint8_t* p = val + nl + 1;
+                size_t rem = vlen - nl - 1;
+                if (rem < 8) { set_error("metadata: truncated"); return HB_EFORMAT; }
+                ix->meta_dims = be32(p);
+                uint32_t items_size = be32(p + 4);
+                p += 8; rem -= 8;
+                if (rem < items_size) { set_error("metadata: truncated items bitmap"); return HB_EFORMAT; }
+                ix->meta_items.clear();
+                if (!roaring_decode(p, items_size, ix->meta_items)) { set_error("metadata: bad roaring bitmap"); return HB_EFORMAT; }
+                p += items_size; rem -= items_size;
+                ix->meta_eps.clear();
+                ix->meta_max_level = 0;
+                if (rem > 0) {
+                    size_t ne = (rem - 1) / 4;
+                    for (size_t i = 0; i < ne; ++i) ix->meta_eps.push_back(le32(p + 4 * i));  // native-endian u32
+                    ix->meta_max_level = p[rem - 1];
+                }
+                ix->have_metadata = true;
+            } else if (item == 1) {  // VersionCodec — src/version.rs:48-59
+                if (vlen < 12) { set_error("version: truncated"); return HB_EFORMAT; }
+                for (int i = 0; i < 3; ++i) ix->version[i] = be32(val + 4 * i);
+            }
+            return HB_OK;
+        }
+        case 1:  // an Updated stone: the index needs a build (reader.rs:407-416)
+            ix->need_build = true;
+            return HB_OK;
+        case 2: {  // Links — src/node.rs:162-165
+            if (vlen < 1 || val[0] != 1) { set_error("links node: bad tag"); return HB_EFORMAT; }
+            std::vector<uint32_t> ids;
+            if (!roaring_decode(val + 1, vlen - 1, ids)) { set_error("links node: bad roaring bitmap"); return HB_EFORMAT; }
+            ix->kv_links[{item, layer}] = std::move(ids);
+            return HB_OK;
+        }
+        case 3: {  // Item — src/node.rs:154-160: [0][header][vector bytes]
+            size_t hs = header_size(ix->metric);
+            if (vlen < 1 + hs || val[0] != 0) { set_error("item node: bad tag or truncated"); return HB_EFORMAT; }
+            size_t vb = vlen - 1 - hs;
+            size_t unit = ix->metric >= HB_HAMMING ? 8 : 4;
+            if (vb % unit) { set_error("item node: %zu trailing bytes", vb % unit); return HB_EFORMAT; }  // SizeMismatch
+            ix->kv_items[item].assign(val + 1, val + vlen);
+            return HB_OK;
+        }
+        default:
+            set_error("Could not convert %u as a `NodeMode`.", (unsigned)mode);
+            return HB_EFORMAT;
+    }
+}
+
+int64_t slot_of(const hb_index* ix, uint32_t id) {
+    auto it = std::lower_bound(ix->ids.begin(), ix->ids.end(), id);
+    return (it != ix->ids.end() && *it == id) ? (int64_t)(it - ix->ids.begin()) : -1;
+}
+
+// Reader::open checks + flatten (reader.rs:387-431)
+hb_status build_host_snapshot_from_kv(hb_index* ix) {
+    if (!ix->have_metadata) { set_error("Metadata are missing on index %u", (unsigned)ix->index); return HB_EMISSING_METADATA; }
+    if (ix->meta_distance != hb_metric_name(ix->metric)) {
+        set_error("Internal error: unmatching distance: expected `%s`, received `%s`", ix->meta_distance.c_str(), hb_metric_name(ix->metric));
+        return HB_EUNMATCHING_DISTANCE;
+    }
+    if (ix->need_build) { set_error("The index %u needs to be built before being read", (unsigned)ix->index); return HB_ENEED_BUILD; }
+    ix->dims = ix->meta_dims;
+    ix->ids = ix->meta_items;  // already ascending
+    size_t n = ix->ids.size();
+    bool bin = ix->metric >= HB_HAMMING;
+    ix->host_row_bytes = bin ? 8 * (((size_t)ix->dims + 63) / 64) : 4 * (size_t)ix->dims;
+    size_t hs = header_size(ix->metric);
+    ix->host_rows.assign(n * ix->host_row_bytes, 0);
+    ix->host_hdr.assign(n, 0.0f);
+    for (size_t s = 0; s < n; ++s) {
+        auto it = ix->kv_items.find(ix->ids[s]);
+        if (it == ix->kv_items.end()) { set_error("item %u listed in metadata has no Item node", ix->ids[s]); return HB_EFORMAT; }
+        const std::vector<uint8_t>& v = it->second;
+        if (v.size() - hs < ix->host_row_bytes) { set_error("item %u: vector shorter than the index dimensions", ix->ids[s]); return HB_EFORMAT; }
+        if (hs == 4) std::memcpy(&ix->host_hdr[s], v.data(), 4);
+        std::memcpy(ix->host_rows.data() + s * ix->host_row_bytes, v.data() + hs, ix->host_row_bytes);
+    }
+    uint32_t n_layers = ix->meta_max_level + 1;
+    for (auto& kv : ix->kv_links) n_layers = std::max(n_layers, kv.first.second + 1);
+    ix->layers.assign(n_layers, HostLayer());
+    std::vector<std::vector<std::pair<uint32_t, const std::vector<uint32_t>*>>> per(n_layers);
+    for (auto& kv : ix->kv_links) {
+        int64_t s = slot_of(ix, kv.first.first);
+        if (s < 0) continue;  // stale links of a deleted item
+        per[kv.first.second].push_back({(uint32_t)s, &kv.second});
+    }
+    for (uint32_t l = 0; l < n_layers; ++l) {
+        HostLayer& hl = ix->layers[l];
+        hl.off.assign(n + 1, 0);
+        for (auto& e : per[l]) hl.off[e.first + 1] = e.second->size();
+        for (size_t s = 0; s < n; ++s) hl.off[s + 1] += hl.off[s];
+        hl.nbr.resize(hl.off[n]);
+        for (auto& e : per[l]) {
+            uint64_t o = hl.off[e.first];
+            for (uint32_t id : *e.second) {
+                int64_t t = slot_of(ix, id);
+                if (t < 0) { set_error("link %u -> %u points to an item that is not in the index", ix->ids[e.first], id); return HB_EFORMAT; }
+                hl.nbr[o++] = (uint32_t)t;
+            }
+        }
+    }
+    ix->eps.clear();
+    for (uint32_t ep : ix->meta_eps) {
+        int64_t s = slot_of(ix, ep);
+        if (s < 0) { set_error("entry point %u is not in the index", ep); return HB_EFORMAT; }
+        ix->eps.push_back((uint32_t)s);
+    }
+    ix->max_level = ix->meta_max_level;
+    ix->kv_items.clear();
+    ix->kv_links.clear();
+    return HB_OK;
+}
+
+// ---- device row layout -------------------------------------------------------------------------------
+int kind_for(hb_metric m, uint32_t dims) {
+    if (m >= HB_HAMMING) return KIND_BIN;
+    if (m == HB_MANHATTAN || dims < 32) return KIND_F32_LANE;
+    return KIND_F32_WARP;
+}
+uint32_t device_row_stride(int kind, uint32_t dims) {
+    if (kind == KIND_BIN) return 16 * ((((dims + 63) / 64) + 1) / 2);
+    if (kind == KIND_F32_LANE) return 16 * ((dims + 3) / 4);
+    uint32_t blocks = dims / 32, chunks = (blocks + 3) / 4, tail = dims % 32;
+    return 4 * (chunks * 128 + 4 * ((tail + 3) / 4));
+}
+void layout_row(int kind, uint32_t dims, const uint8_t* natural, uint8_t* out) {
+    uint32_t stride = device_row_stride(kind, dims);
+    std::memset(out, 0, stride);
+    if (kind == KIND_BIN) { std::memcpy(out, natural, 8 * (((size_t)dims + 63) / 64)); return; }
+    if (kind == KIND_F32_LANE) { std::memcpy(out, natural, 4 * (size_t)dims); return; }
+    const float* src = (const float*)natural;
+    float* dst = (float*)out;
+    uint32_t blocks = dims / 32, chunks = (blocks + 3) / 4, main = blocks * 32;
+    for (uint32_t e = 0; e < main; ++e) {
+        uint32_t blk = e >> 5, j = e & 31;
+        float v;
+        std::memcpy(&v, natural + 4 * (size_t)e, 4);
+        dst[(blk >> 2) * 128 + j * 4 + (blk & 3)] = v;
+    }
+    (void)src;
+    std::memcpy(dst + chunks * 128, natural + 4 * (size_t)main, 4 * (size_t)(dims - main));
+}
+
+}  // namespace hb

@@ -1,0 +1,82 @@
+"""GPU parity: the CUDA engine, called through the C-ABI, against the CPU oracle on the same graphs.
+Bit-exact ids AND distance bits for every metric (the kernels reproduce the reference's summation order)."""
+import numpy as np
+import pytest
+
+from helpers import assert_counters_same, assert_same, make_db, make_vectors, open_reader_arrays, open_reader_kv
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # metric, n, dims, kind
+    ("euclidean", 3000, 128, "uniform"),
+    ("euclidean", 1500, 100, "clustered"),   # AVX main part + 4-element scalar tail
+    ("euclidean", 800, 20, "uniform"),       # SSE path
+    ("euclidean", 500, 7, "uniform"),        # scalar path
+    ("cosine", 2000, 96, "clustered"),
+    ("cosine", 1000, 45, "uniform"),
+    ("cosine", 600, 24, "uniform"),
+    ("cosine", 400, 3, "uniform"),
+    ("manhattan", 1200, 64, "uniform"),
+    ("manhattan", 500, 10, "int"),
+    ("hamming", 2000, 256, "uniform"),
+    ("hamming", 700, 70, "uniform"),
+    ("binary quantized cosine", 2000, 1024, "clustered"),
+    ("binary quantized cosine", 900, 100, "uniform"),
+    ("binary quantized euclidean", 1000, 192, "uniform"),
+    ("binary quantized manhattan", 1000, 65, "uniform"),
+]
+
+
+@pytest.mark.parametrize("metric,n,dims,kind", CASES)
+def test_by_vector_matches_oracle(metric, n, dims, kind):
+    db, x = make_db(metric, n, dims, seed=n + dims, kind=kind)
+    rd = open_reader_arrays(db, metric)
+    q = make_vectors(64, dims, seed=7, kind=kind)
+    q[:8] = x[:8]  # self queries
+    for count, ef in [(10, 64), (1, 1), (10, 10), (100, 100), (5, 200)]:
+        want = db.search_by_vector(q, count, ef=max(ef, count), counters=True)
+        got = rd.nns(count).ef_search(ef).by_vectors_raw(q, counters=True)
+        assert_same(got, want, f"{metric} n={n} d={dims} k={count} ef={ef}")
+        assert_counters_same(got[3], want[3], f"{metric} k={count} ef={ef}")
+
+
+@pytest.mark.parametrize("metric,n,dims,kind", CASES[::3])
+def test_by_item_matches_oracle(metric, n, dims, kind):
+    db, x = make_db(metric, n, dims, seed=n + dims + 1, kind=kind)
+    rd = open_reader_arrays(db, metric)
+    items = np.array([0, 1, 5, n - 1, n + 10, 17], np.uint32)  # n+10 is absent -> None
+    for count, ef in [(10, 64), (3, 3)]:
+        want = db.search_by_item(items, count, ef=max(ef, count), counters=True)
+        got = rd.nns(count).ef_search(ef).by_items_raw(items, counters=True)
+        assert_same(got, want, f"by_item {metric}")
+        assert got[2][4] == 0xFFFFFFFF
+        for i in (0, 1, 2, 3, 5):
+            assert items[i] not in got[0][i, :got[2][i]]
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "cosine", "hamming", "binary quantized cosine"])
+def test_kv_route_equals_array_route(metric):
+    n, dims = 700, 40
+    ids = np.sort(np.random.default_rng(3).choice(2_000_000, n, replace=False)).astype(np.uint32)
+    ids[-1] = 0xFFFFFFFF  # sparse ids up to u32::MAX (src/tests/writer.rs:88-107)
+    db, x = make_db(metric, n, dims, seed=11, ids=ids)
+    ra = open_reader_arrays(db, metric)
+    rk = open_reader_kv(db, metric, index=3)
+    q = make_vectors(32, dims, seed=5)
+    want = db.search_by_vector(q, 10, ef=50)
+    assert_same(ra.nns(10).ef_search(50).by_vectors_raw(q), want, "arrays")
+    assert_same(rk.nns(10).ef_search(50).by_vectors_raw(q), want, "kv")
+    assert rk.n_items() == n and rk.dimensions() == dims and rk.version() == (0, 1, 3)
+    assert np.array_equal(rk.item_ids(), ids)
+
+
+def test_config1_shape():
+    """BASELINE config 1: 10k x 128 Euclidean, M=16/M0=32, efC=100, 1k queries, top-10, ef=64."""
+    db, x = make_db("euclidean", 10000, 128, seed=1, n_threads=8)
+    rd = open_reader_arrays(db, "euclidean")
+    q = make_vectors(1000, 128, seed=2)
+    want = db.search_by_vector(q, 10, ef=64, counters=True, n_threads=8)
+    got = rd.nns(10).ef_search(64).by_vectors_raw(q, counters=True)
+    assert_same(got, want, "config 1")
+    assert_counters_same(got[3], want[3], "config 1")
