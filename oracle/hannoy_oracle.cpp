@@ -950,6 +950,20 @@ int orc_db_set_links(void* h, uint32_t id, uint32_t level, const uint32_t* nbrs,
     db.links_dirty = true;
     return 0;
 }
+// install one whole layer as CSR (offsets in slot order, neighbours as item ids) — graph cache reload
+int orc_db_set_csr(void* h, uint32_t level, const uint64_t* off, const uint32_t* nbr_ids, uint64_t nnz) {
+    Db& db = *(Db*)h;
+    db.commit();
+    size_t N = db.n();
+    if (db.layers.size() <= level) db.layers.resize(level + 1);
+    for (auto& ly : db.layers) if (ly.off.size() != N + 1) { ly.off.assign(N + 1, 0); ly.has.assign(N, 0); ly.nbr.clear(); }
+    auto& ly = db.layers[level];
+    ly.off.assign(off, off + N + 1);
+    ly.nbr.resize(nnz);
+    for (uint64_t i = 0; i < nnz; ++i) { int64_t s = db.slot_of(nbr_ids[i]); if (s < 0) return 1; ly.nbr[i] = (uint32_t)s; }
+    for (size_t s = 0; s < N; ++s) ly.has[s] = ly.off[s + 1] > ly.off[s];
+    return 0;
+}
 int orc_db_set_entry_points(void* h, const uint32_t* eps, uint32_t n, uint32_t max_level) {
     Db& db = *(Db*)h;
     db.commit();

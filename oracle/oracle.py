@@ -42,6 +42,7 @@ def lib():
             "orc_db_build": (i32, [vp, u32, u32, u32, f32, u64, i32]),
             "orc_db_set_links": (i32, [vp, u32, u32, vp, u32]),
             "orc_db_set_entry_points": (i32, [vp, vp, u32, u32]),
+            "orc_db_set_csr": (i32, [vp, u32, vp, vp, u64]),
             "orc_db_n_items": (u64, [vp]), "orc_db_row_bytes": (u64, [vp]), "orc_db_max_level": (u32, [vp]),
             "orc_db_n_entry_points": (u32, [vp]), "orc_db_get_entry_points": (None, [vp, vp]),
             "orc_db_get_ids": (None, [vp, vp]), "orc_db_get_rows": (None, [vp, vp]),
