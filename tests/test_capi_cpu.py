@@ -1,0 +1,152 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/hannoy_b200.h declares,
+decodes the reference's KV encoding, applies the Reader::open checks, and refuses to compute without a GPU
+(no CPU fallback).  No kernel is launched here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import make_db
+from hannoy_b200 import _lib as L
+import hannoy_b200 as hb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "hannoy_b200.h")).read()
+    declared = set(re.findall(r"\b(hb_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
+    lib = C.CDLL(L.SO_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_metric_names_are_the_reference_strings():
+    names = ["euclidean", "cosine", "manhattan", "hamming", "binary quantized cosine", "binary quantized euclidean",
+             "binary quantized manhattan"]
+    for i, n in enumerate(names):
+        assert L.lib().hb_metric_name(i).decode() == n
+        assert L.lib().hb_metric_from_name(n.encode()) == i
+    assert L.lib().hb_metric_from_name(b"dot") == -1
+
+
+def _begin(metric_id, index=0):
+    h = C.c_void_p()
+    assert L.lib().hb_index_begin(metric_id, index, C.byref(h)) == L.HB_OK
+    return h
+
+
+def _push_all(h, kv):
+    for k, v in kv:
+        st = L.lib().hb_index_push_kv(h, k, len(k), v, len(v))
+        assert st == L.HB_OK, L.lib().hb_last_error()
+
+
+def test_open_checks_missing_metadata_unmatching_distance_need_build():
+    db, _ = make_db("cosine", 50, 12, seed=1)
+    kv = db.export_kv(0)
+    lib = L.lib()
+    # MissingMetadata — reader.rs:390-393
+    h = _begin(1)
+    _push_all(h, [p for p in kv if p[0][2] != 0])
+    assert lib.hb_index_finalize(h, 0) == L.HB_EMISSING_METADATA
+    lib.hb_index_free(h)
+    # UnmatchingDistance — reader.rs:400-405
+    h = _begin(0)
+    _push_all(h, kv)
+    assert lib.hb_index_finalize(h, 0) == L.HB_EUNMATCHING_DISTANCE
+    assert b"unmatching distance" in lib.hb_last_error()
+    lib.hb_index_free(h)
+    # NeedBuild: an Updated stone is present — reader.rs:407-416
+    h = _begin(1)
+    _push_all(h, kv + [(bytes([0, 0, 1, 0, 0, 0, 9, 0]), bytes([0]))])
+    assert lib.hb_index_finalize(h, 0) == L.HB_ENEED_BUILD
+    lib.hb_index_free(h)
+    # pairs of another index are ignored -> metadata missing for index 5
+    h = _begin(1, index=5)
+    _push_all(h, kv)
+    assert lib.hb_index_finalize(h, 0) == L.HB_EMISSING_METADATA
+    lib.hb_index_free(h)
+
+
+def test_bad_pairs_are_rejected():
+    lib = L.lib()
+    h = _begin(0)
+    assert lib.hb_index_push_kv(h, b"short", 5, b"x", 1) == L.HB_EFORMAT
+    assert lib.hb_index_push_kv(h, bytes([0, 0, 9, 0, 0, 0, 0, 0]), 8, b"x", 1) == L.HB_EFORMAT   # unknown NodeMode
+    assert lib.hb_index_push_kv(h, bytes([0, 0, 2, 0, 0, 0, 0, 0]), 8, bytes([1, 9, 9, 9]), 4) == L.HB_EFORMAT  # bad roaring
+    assert lib.hb_index_push_kv(h, bytes([0, 0, 3, 0, 0, 0, 0, 0]), 8, bytes([0, 0, 0, 0, 0, 1, 2]), 7) == L.HB_EFORMAT  # SizeMismatch
+    lib.hb_index_free(h)
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "cosine", "hamming", "binary quantized cosine"])
+def test_kv_decode_matches_what_was_written(metric):
+    """push_kv + the host half of finalize reproduce ids / dims / entry points / vectors; without a GPU finalize then
+    stops with HB_ECUDA and search refuses to run."""
+    n, dims = 300, 70
+    ids = np.sort(np.random.default_rng(4).choice(1 << 30, n, replace=False)).astype(np.uint32)
+    db, x = make_db(metric, n, dims, seed=3, ids=ids)
+    lib = L.lib()
+    mid = hb.reader._distance_of(metric).ID
+    h = _begin(mid, index=2)
+    _push_all(h, db.export_kv(2))
+    st = lib.hb_index_finalize(h, 0)
+    if _has_gpu():
+        assert st == L.HB_OK
+    else:
+        assert st == L.HB_ECUDA, "the product must fail loudly without a CUDA device"
+        assert b"no CUDA device" in lib.hb_last_error()
+    assert lib.hb_index_n_items(h) == n and lib.hb_index_dimensions(h) == dims
+    assert lib.hb_index_max_level(h) == db.max_level
+    assert lib.hb_index_n_entry_points(h) == len(db.entry_points)
+    got = np.zeros(n, np.uint32)
+    lib.hb_index_item_ids(h, got.ctypes.data_as(C.c_void_p), n)
+    assert np.array_equal(got, ids)
+    v = np.zeros(dims, np.float32)
+    for s in (0, 17, n - 1):
+        assert lib.hb_index_item_vector(h, int(ids[s]), v.ctypes.data_as(C.c_void_p)) == L.HB_OK
+        if metric in ("euclidean", "cosine"):
+            assert np.array_equal(v, x[s])
+        elif metric == "hamming":
+            assert np.array_equal(v, (x[s] > 0).astype(np.float32))
+        else:
+            assert np.array_equal(v, np.where(np.signbit(x[s]), -1.0, 1.0).astype(np.float32))
+    assert lib.hb_index_contains_item(h, int(ids[3])) == 1 and lib.hb_index_contains_item(h, int(ids[3]) + 1) in (0, 1)
+    if not _has_gpu():
+        out = np.zeros(10, np.uint32)
+        q = np.zeros(dims, np.float32)
+        st = lib.hb_search_by_vector(h, q.ctypes.data_as(C.c_void_p), 1, dims, 10, 100, None, out.ctypes.data_as(C.c_void_p),
+                                     out.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), None)
+        assert st == L.HB_ESTATE  # not finalized -> no search, and no CPU path to fall back to
+    lib.hb_index_free(h)
+
+
+def test_python_mirror_surface():
+    """The host mirror keeps the reference names: Reader.open/nns, QueryBuilder.ef_search/candidates/linear_below(_ratio)/
+    by_vector/by_item, Searched.into_nns/did_cancel, and the defaults of reader.rs:23-32."""
+    for name in ("open", "nns", "dimensions", "n_entrypoints", "n_items", "item_ids", "index", "version", "item_vector",
+                 "is_empty", "contains_item"):
+        assert hasattr(hb.Reader, name)
+    for name in ("ef_search", "candidates", "linear_below", "linear_below_ratio", "by_vector", "by_item",
+                 "by_vector_with_cancellation", "by_item_with_cancellation"):
+        assert hasattr(hb.QueryBuilder, name)
+    qb = hb.QueryBuilder(None, 150)
+    assert qb.ef == 100 and qb._linear_below == 1000 and qb._linear_below_ratio == 1.0
+    assert qb.ef_search(20).ef == 150        # ef_search stores max(ef, count) — reader.rs:217-220
+    assert qb.ef_search(300).ef == 300
+    with pytest.raises(AssertionError):
+        qb.linear_below_ratio(1.5)
+    s = hb.Searched([(1, 0.5)], False)
+    assert s.into_nns() == [(1, 0.5)] and s.did_cancel() is False
+    assert [d.name() for d in (hb.Euclidean, hb.Cosine, hb.Manhattan, hb.Hamming)] == ["euclidean", "cosine", "manhattan", "hamming"]
