@@ -1,37 +1,59 @@
-"""Builds libhannoy_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
+"""Builds libhannoy_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo).
+
+`python -m hannoy_b200.build [--force] [-v] [--variant phases]`; the `phases` variant (dev only) adds
+-DHB_PHASES (per-phase cycle counters in the search kernel) and is written to libhannoy_b200_phases.so,
+loaded instead of the product library when HB_LIB_VARIANT=phases.
+"""
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libhannoy_b200.so")
 SOURCES = ["capi.cu", "search.cu", "exact.cu", "snapshot.cpp"]
-HEADERS = ["common.h", "dist.cuh", "sorted.cuh", os.path.join("..", "..", "include", "hannoy_b200.h")]
+HEADERS = ["common.h", "dist.cuh", "sorted.cuh", "ring.cuh", os.path.join("..", "..", "include", "hannoy_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # bit-exactness: no implicit FMA contraction, IEEE div/sqrt, no flush-to-zero
-    "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-    "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-shared", "-cudart", "static",
+    "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false", "-split-compile", "0",
+    "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function",
 ]
+VARIANTS = {"": [], "phases": ["-DHB_PHASES"]}
 
 
-def needs_build():
-    if not os.path.exists(OUT):
+def out_path(variant=""):
+    return os.path.join(HERE, f"libhannoy_b200{'_' + variant if variant else ''}.so")
+
+
+def needs_build(variant=""):
+    out = out_path(variant)
+    if not os.path.exists(out):
         return True
-    t = os.path.getmtime(OUT)
+    t = os.path.getmtime(out)
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
-    subprocess.check_call(cmd)
-    return OUT
+def build(force=False, verbose=False, variant=""):
+    out = out_path(variant)
+    if not force and not needs_build(variant):
+        return out
+    objdir = os.path.join(HERE, "build", variant or "product")
+    os.makedirs(objdir, exist_ok=True)
+    flags = FLAGS + VARIANTS[variant] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        subprocess.check_call([NVCC] + flags + ["-c", os.path.join(CSRC, src), "-o", obj])
+        return obj
+
+    with ThreadPoolExecutor(len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static"] + objs + ["-o", out])
+    return out
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(OUT)
+    variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else ""
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=variant))

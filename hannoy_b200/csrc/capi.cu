@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cctype>
 #include <cstring>
 
 #include "common.h"
@@ -22,6 +23,23 @@ using namespace hb;
             return HB_ECUDA;                                                             \
         }                                                                                \
     } while (0)
+
+// ---- runtime tunables: hb_tune(key, value) wins over the environment variable HB_<KEY> ---------------------
+static std::mutex g_tune_mu;
+static std::map<std::string, int> g_tune;
+namespace hb {
+int tunable(const char* key, int dflt) {
+    {
+        std::lock_guard<std::mutex> g(g_tune_mu);
+        auto it = g_tune.find(key);
+        if (it != g_tune.end()) return it->second;
+    }
+    std::string env = "HB_";
+    for (const char* c = key; *c; ++c) env.push_back((char)std::toupper((unsigned char)*c));
+    const char* v = std::getenv(env.c_str());
+    return v ? std::atoi(v) : dflt;
+}
+}  // namespace hb
 
 static const char* kMetricNames[] = {"euclidean", "cosine", "manhattan", "hamming", "binary quantized cosine",
                                      "binary quantized euclidean", "binary quantized manhattan"};
@@ -65,6 +83,13 @@ int hb_metric_from_name(const char* name) {
 }
 const char* hb_last_error(void) { return last_error(); }
 uint64_t hb_launch_count(void) { return g_launches; }
+void hb_debug_phases(uint64_t* out8) { if (out8) read_phases((unsigned long long*)out8); }
+hb_status hb_tune(const char* key, int value) {
+    if (!key) return HB_EINVAL;
+    std::lock_guard<std::mutex> g(g_tune_mu);
+    g_tune[key] = value;
+    return HB_OK;
+}
 
 hb_status hb_index_begin(hb_metric m, uint16_t index, hb_index** out) {
     if (!out || (int)m < 0 || (int)m > 6) { set_error("hb_index_begin: bad arguments"); return HB_EINVAL; }
@@ -215,6 +240,17 @@ hb_status hb_index_finalize(hb_index* ix, int device) {
         if ((st = upload(ix, off32.data(), off32.size(), &d.off[l])) != HB_OK) return st;
         if ((st = upload(ix, hl.nbr.data(), hl.nbr.size(), &d.nbr[l])) != HB_OK) return st;
     }
+    if (d.n_layers && n && tunable("fixed_adjacency", 1)) {
+        const HostLayer& l0 = ix->layers[0];
+        uint64_t max_deg = 0;
+        for (size_t i = 0; i < n; ++i) max_deg = std::max<uint64_t>(max_deg, l0.off[i + 1] - l0.off[i]);
+        if (max_deg <= FIXED_DEG) {
+            std::vector<uint32_t> fx(n * (size_t)FIXED_DEG, 0xffffffffu);
+            for (size_t i = 0; i < n; ++i)
+                std::copy(l0.nbr.begin() + l0.off[i], l0.nbr.begin() + l0.off[i + 1], fx.begin() + i * FIXED_DEG);
+            if ((st = upload(ix, fx.data(), fx.size(), &d.nbr0x)) != HB_OK) return st;
+        }
+    }
     if ((st = upload(ix, ix->eps.data(), ix->eps.size(), &d.eps)) != HB_OK) return st;
     d.n_ep = (uint32_t)ix->eps.size();
     ix->finalized = true;
@@ -277,21 +313,17 @@ hb_status hb_index_item_vector(const hb_index* ix, uint32_t item, float* out) {
 }  // extern "C"
 
 // ---- workspaces ---------------------------------------------------------------------------------------
-static int env_int(const char* name, int dflt) {
-    const char* v = std::getenv(name);
-    return v ? std::atoi(v) : dflt;
-}
-
 static hb_status make_workspace(hb_index* ix, Workspace** out) {
     Workspace* w = new Workspace();
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, ix->device));
-    int bps = std::max(1, std::min(16, env_int("HB_BLOCKS_PER_SM", 4)));
+    int bps = 64 / SEARCH_WARPS_PER_BLOCK;  // one visited bitset per warp the hardware can keep resident
+    w->n_sm = prop.multiProcessorCount;
     w->n_slots = prop.multiProcessorCount * bps * SEARCH_WARPS_PER_BLOCK;
     size_t n = ix->ids.size();
     w->vis_words = (uint32_t)(((n + 31) / 32 + 31) / 32 * 32);
     if (w->vis_words == 0) w->vis_words = 32;
-    w->touched_cap = (uint32_t)std::max(1024, env_int("HB_TOUCHED_CAP", 16384));
+    w->touched_cap = (uint32_t)std::max(1024, tunable("touched_cap", 16384));
     CUDA_TRY(cudaMalloc(&w->visited, (size_t)w->n_slots * w->vis_words * 4));
     CUDA_TRY(cudaMemset(w->visited, 0, (size_t)w->n_slots * w->vis_words * 4));
     CUDA_TRY(cudaMalloc(&w->touched, (size_t)w->n_slots * w->touched_cap * 4));
@@ -358,25 +390,43 @@ static hb_status run_search(const hb_index* ix, Workspace* w, SearchParams base,
     base.n_work = (uint32_t)nq;
     base.q_smem_bytes = (d.row_stride + 15) & ~15u;
     const uint32_t ef0 = std::max(base.ef_raw, base.count);
+    if (d.kind == KIND_F32_WARP) {
+        // rows in flight per warp: as many as fit the ring budget, in whole reduction groups
+        uint32_t budget = (uint32_t)std::max(0, tunable("ring_bytes", 12288));
+        uint32_t slots = budget / d.row_stride / ROW_GROUP * ROW_GROUP;
+        slots = std::max<uint32_t>(ROW_GROUP, std::min<uint32_t>(slots, 32));
+        base.ring_slots = slots;
+        base.ring_stride = d.row_stride;
+        SearchParams probe = base;
+        probe.pass = 1;
+        if (search_smem_per_warp(probe) * SEARCH_WARPS_PER_BLOCK > (size_t)SEARCH_MAX_SMEM) {
+            base.ring_slots = 0;  // rows too long to stage: direct global-memory gather
+            base.ring_stride = 0;
+        }
+    }
     SearchParams fast = base, slow = base;
     if (base.mode >= 2) {
         fast.res_cap = (base.count + 32 + 31) & ~31u;
         fast.q_cap = 0;
     } else {
+        // live queue entries are a subset of the result set (+ distance ties) once the result set is full:
+        // dead ones are dropped by queue_push, so the queue needs little more room than the result set
         fast.res_cap = (std::max(ef0, d.n_ep) + 32 + 31) & ~31u;
-        fast.q_cap = (std::max(2 * ef0, d.n_ep) + 64 + 31) & ~31u;
+        fast.q_cap = (std::max(ef0, d.n_ep) + 64 + 31) & ~31u;
     }
     fast.pass = 0;
-    size_t per_block = search_smem_per_warp(fast) * SEARCH_WARPS_PER_BLOCK;
-    int blocks_fast = w->n_slots / SEARCH_WARPS_PER_BLOCK;
-    if (per_block > (size_t)SEARCH_MAX_SMEM) {
+    int bps_fast = search_blocks_per_sm(fast);
+    if (bps_fast == 0) {
         fast.res_cap = 0; fast.q_cap = 0;  // every query takes the global-memory pass
     }
     slow.pass = 1;
     slow.gheap = (unsigned long long*)w->gheap;
     uint64_t half = w->gheap_entries_per_slot / 2;
     slow.res_cap = (uint32_t)half; slow.q_cap = (uint32_t)half;
-    if ((size_t)slow.q_smem_bytes * SEARCH_WARPS_PER_BLOCK > (size_t)SEARCH_MAX_SMEM) { set_error("dimension too large"); return HB_EINVAL; }
+    int bps_slow = search_blocks_per_sm(slow);
+    if (bps_slow == 0) { set_error("dimension too large"); return HB_EINVAL; }
+    int bps_cap = std::max(1, tunable("blocks_per_sm", 64));
+    int blocks_fast = std::min(w->n_slots / SEARCH_WARPS_PER_BLOCK, w->n_sm * std::max(std::min(bps_fast, bps_cap), 1));
     int blocks_slow = w->slow_slots / SEARCH_WARPS_PER_BLOCK;
     return launch_search(fast, slow, blocks_fast, blocks_slow, stream);
 }

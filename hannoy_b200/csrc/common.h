@@ -48,7 +48,11 @@ struct DevIndex {
     const uint32_t* nbr[MAX_LEVELS] = {};  // per layer: neighbour SLOTS, ascending in each list
     const uint32_t* eps = nullptr;         // entry point slots, metadata order
     uint32_t n_ep = 0;
+    // layer 0 again, fixed stride: FIXED_DEG slots per item, ascending, padded with UINT32_MAX — one aligned
+    // 128-byte line per expansion instead of two dependent CSR reads.  nullptr if some layer-0 list is longer.
+    const uint32_t* nbr0x = nullptr;
 };
+constexpr uint32_t FIXED_DEG = 32;
 
 // One search call.
 struct SearchParams {
@@ -78,7 +82,10 @@ struct SearchParams {
     int pass = 0;                      // 0 = shared-memory heaps, 1 = global-memory heaps over overflow_list
     uint32_t n_work = 0;               // pass 0: nq ; pass 1: read from *n_overflow on device
     uint32_t q_smem_bytes = 0;         // per-warp query staging bytes
+    uint32_t ring_slots = 0;           // KIND_F32_WARP: rows in flight per warp (multiple of ROW_GROUP), ring.cuh
+    uint32_t ring_stride = 0;          // bytes between ring slots
 };
+constexpr int ROW_GROUP = 4;           // rows reduced together by one warp
 
 // ---- host-side snapshot -----------------------------------------------------------------------
 struct HostLayer {
@@ -88,6 +95,7 @@ struct HostLayer {
 
 struct Workspace {
     int n_slots = 0;
+    int n_sm = 0;
     uint32_t* visited = nullptr;
     uint32_t vis_words = 0;
     uint32_t* touched = nullptr;
@@ -154,12 +162,16 @@ void layout_row(int kind, uint32_t dims, const uint8_t* natural, uint8_t* out);
 int kind_for(hb_metric m, uint32_t dims);
 // search.cu
 constexpr int SEARCH_WARPS_PER_BLOCK = 4;
-constexpr int SEARCH_MAX_SMEM = 200 * 1024;
+constexpr int SEARCH_MAX_SMEM = 226 * 1024;  // per SM (227 KB usable, 1 KB reserved per resident CTA)
 hb_status launch_search(const SearchParams& fast, const SearchParams& slow, int blocks_fast, int blocks_slow, void* stream);
 size_t search_smem_per_warp(const SearchParams& p);
+int search_blocks_per_sm(const SearchParams& p);  // resident CTAs per SM for these parameters
+// runtime tunables (hb_tune): ring bytes per warp, max resident CTAs per SM, ...
+int tunable(const char* key, int dflt);
 // exact.cu
 hb_status launch_exact_knn(const DevIndex& ix, const float* d_q, uint64_t nq, uint32_t k, uint32_t* d_ids, float* d_dist, void* stream);
 hb_status launch_merge_topk(const uint32_t* d_ids, const float* d_dist, uint32_t n_parts, uint64_t nq, uint32_t k,
                             uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len, void* stream);
 extern unsigned long long g_launches;
+void read_phases(unsigned long long* out);
 }  // namespace hb

@@ -58,7 +58,9 @@ __device__ __forceinline__ float finish_bin(int metric, uint32_t h, uint32_t L, 
 // ---- KIND_F32_WARP ---------------------------------------------------------------------------------
 // Raw euclid-sum / dot of up to R rows against the warp's query (in shared memory, same permuted
 // layout).  Returns the final reduced value of row r in out[r] on every lane.
-template <int R, bool DOT>
+// ROWS_SMEM: the rows were staged in shared memory by the bulk-copy ring (ring.cuh); else they are read from
+// global memory with 128-bit loads.
+template <int R, bool DOT, bool ROWS_SMEM>
 __device__ __forceinline__ void warp_rows_raw(const DevIndex& ix, const float* qs, const uint8_t* const (&rowp)[R], float (&out)[R]) {
     const int lane = lane_id();
     float acc[R];
@@ -68,7 +70,10 @@ __device__ __forceinline__ void warp_rows_raw(const DevIndex& ix, const float* q
     for (uint32_t c = 0; c < ix.n_chunks; ++c) {
         float4 v[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = __ldg(reinterpret_cast<const float4*>(rowp[r]) + c * 32 + lane);
+        for (int r = 0; r < R; ++r) {
+            const float4* p4 = reinterpret_cast<const float4*>(rowp[r]) + c * 32 + lane;
+            v[r] = ROWS_SMEM ? *p4 : __ldg(p4);
+        }
         float4 qv = q4[c * 32 + lane];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -94,7 +99,7 @@ __device__ __forceinline__ void warp_rows_raw(const DevIndex& ix, const float* q
         const float* rt = reinterpret_cast<const float*>(rowp[r]) + ix.tail_off;
         const float* qt = qs + ix.tail_off;
         for (uint32_t e = 0; e < ix.tail; ++e) {
-            float a = qt[e], b = __ldg(rt + e);
+            float a = qt[e], b = ROWS_SMEM ? rt[e] : __ldg(rt + e);
             if (DOT) res = __fadd_rn(res, __fmul_rn(a, b));
             else { float d = __fsub_rn(a, b); res = __fadd_rn(res, __fmul_rn(d, d)); }
         }

@@ -92,8 +92,8 @@ __global__ void __launch_bounds__(EX_WARPS * 32) exact_knn_kernel(const __grid_c
             for (int t = 0; t < tq; ++t) {
                 float raw[4];
                 const float* qs = qs_all + (size_t)t * qstride / 4;
-                if (ix.metric == HB_COSINE) warp_rows_raw<4, true>(ix, qs, rowp, raw);
-                else warp_rows_raw<4, false>(ix, qs, rowp, raw);
+                if (ix.metric == HB_COSINE) warp_rows_raw<4, true, false>(ix, qs, rowp, raw);
+                else warp_rows_raw<4, false, false>(ix, qs, rowp, raw);
                 int len = mylen[t];
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {

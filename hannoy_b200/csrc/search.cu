@@ -6,17 +6,36 @@
 //     tuple order (src/ordered_float.rs:25-29), slots being order-isomorphic to ItemIds;
 //   * the visited set (`path: RoaringBitmap`, reader.rs:734) is an exact per-warp bitset in global
 //     memory, cleared through a touched list;
-//   * neighbour rows are gathered with coalesced 128-bit loads, reduced with warp shuffles in the
-//     AVX lane order so distances are bit-identical to the reference (dist.cuh);
+//   * f32 neighbour rows are gathered by the bulk async-copy engine (one `cp.async.bulk` per row, posted by
+//     the lane that owns the neighbour, landing in a per-warp shared-memory ring behind mbarriers, ring.cuh)
+//     so a warp keeps ring_slots x row_bytes in flight without registers; binary codes are read with
+//     128-bit loads, one row per lane.  Distances are reduced with warp shuffles in the AVX lane order so
+//     they are bit-identical to the reference (dist.cuh);
+//   * layer-0 adjacency is read from a fixed-stride copy (one aligned 128-byte line per expansion) and the
+//     line of the most likely next candidate is requested while the current rows are in flight;
 //   * queries whose heaps outgrow shared memory are re-run by a second pass of the same code with
 //     heaps in global memory (never on the CPU).
 #include <cfloat>
 #include <cstdio>
 
 #include "dist.cuh"
+#include "ring.cuh"
 #include "sorted.cuh"
 
 namespace hb {
+
+// Optional phase timers (build with -DHB_PHASES; dev only): cycles per phase summed over all queries.
+__device__ unsigned long long g_phase[16];
+#ifdef HB_PHASES
+#define PH_DECL long long ph_t = clock64();
+#define PH_ADD(c, i) { long long ph_n = clock64(); (c).ph[i] += ph_n - ph_t; ph_t = ph_n; }
+#define PH_RESET ph_t = clock64();
+#else
+#define PH_DECL
+#define PH_ADD(c, i) {}
+#define PH_RESET
+#endif
+enum { PH_STAGE = 0, PH_UPPER = 1, PH_ADJ = 2, PH_VIS = 3, PH_ROWS = 4, PH_HEAP = 5, PH_TAIL = 6, PH_TOTAL = 7, PH_N = 8 };
 
 struct Ctx {
     const SearchParams& p;
@@ -26,8 +45,13 @@ struct Ctx {
     const float* qs; float qn;            // query (device layout) in shared memory, query header norm
     uint32_t excl;                        // by_item: slot removed from the candidates, else UINT32_MAX
     bool overflow;
-    u64 n_dist[2], n_exp[2], n_deg[2];    // [0]=upper layers, [1]=layer 0
-    __device__ Ctx(const SearchParams& pp) : p(pp) {}
+    RowRing& ring;                        // per-warp, lives across queries (barrier phases persist)
+#ifdef HB_PHASES
+    long long ph[PH_N];
+#endif
+    uint32_t cur_dist, cur_exp, cur_deg;  // counters of the visit in progress
+    u64 n_dist_up, n_exp_up, n_deg_up, n_dist_l0, n_exp_l0, n_deg_l0;
+    __device__ Ctx(const SearchParams& pp, RowRing& rr) : p(pp), ring(rr) {}
 };
 
 __device__ __forceinline__ float key_dist(u64 k) { return __uint_as_float((uint32_t)(k >> 32)); }
@@ -125,11 +149,13 @@ __device__ __forceinline__ bool passes_filter(const Ctx& c, uint32_t s, bool fil
 }
 
 // ---- distances of one chunk (<= 32 rows, one per lane) -----------------------------------------------------
-__device__ __forceinline__ float chunk_distances(const Ctx& c, unsigned mask, uint32_t s) {
+template <int KIND>
+__device__ __forceinline__ float chunk_distances(Ctx& c, unsigned mask, uint32_t s) {
     const DevIndex& ix = c.p.ix;
     const int lane = lane_id();
     float mine = 0.0f;
-    if (ix.kind == KIND_F32_WARP) {
+    if (KIND == KIND_F32_WARP && c.ring.slots == 0) {
+        // rows too long for the shared-memory ring: 4 rows at a time straight from global memory
         unsigned m = mask;
         while (m) {
             int l[4];
@@ -142,8 +168,8 @@ __device__ __forceinline__ float chunk_distances(const Ctx& c, unsigned mask, ui
                 rowp[r] = ix.rows + (size_t)sl[r] * ix.row_stride;
             }
             float raw[4];
-            if (ix.metric == HB_COSINE) warp_rows_raw<4, true>(ix, c.qs, rowp, raw);
-            else warp_rows_raw<4, false>(ix, c.qs, rowp, raw);
+            if (ix.metric == HB_COSINE) warp_rows_raw<4, true, false>(ix, c.qs, rowp, raw);
+            else warp_rows_raw<4, false, false>(ix, c.qs, rowp, raw);
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 if (lane == l[r]) {
@@ -152,7 +178,38 @@ __device__ __forceinline__ float chunk_distances(const Ctx& c, unsigned mask, ui
                 }
             }
         }
-    } else if (ix.kind == KIND_F32_LANE) {
+    } else if (KIND == KIND_F32_WARP) {
+        // Row r (in ascending-lane order) lands in ring slot r % S.  The first S copies are posted at once by
+        // the lanes that own them; slot group g is re-posted as soon as its ROW_GROUP rows were consumed.
+        const int S = (int)c.ring.slots;
+        const int n_live = __popc(mask);
+        const bool has = (mask >> lane) & 1;
+        const int rank = __popc(mask & ((1u << lane) - 1));
+        const uint8_t* grow = ix.rows + (size_t)s * ix.row_stride;
+        if (has && rank < S) c.ring.post(rank, grow, ix.row_stride);
+        const float in = (has && ix.metric == HB_COSINE) ? __ldg(&ix.hdr[s]) : 0.0f;
+        int slot0 = 0;
+        for (int r0 = 0; r0 < n_live; r0 += ROW_GROUP) {
+            const int g = min(ROW_GROUP, n_live - r0);
+            const uint8_t* rowp[ROW_GROUP];
+#pragma unroll
+            for (int r = 0; r < ROW_GROUP; ++r) {
+                if (r < g) c.ring.wait(slot0 + r);
+                rowp[r] = c.ring.ptr + (size_t)(slot0 + (r < g ? r : 0)) * c.ring.stride;
+            }
+            float raw[ROW_GROUP];
+            if (ix.metric == HB_COSINE) warp_rows_raw<ROW_GROUP, true, true>(ix, c.qs, rowp, raw);
+            else warp_rows_raw<ROW_GROUP, false, true>(ix, c.qs, rowp, raw);
+            __syncwarp();  // every lane has read the group's slots: they may be overwritten
+            const int nxt = rank - r0 - S;
+            if (has && nxt >= 0 && nxt < g) c.ring.post(slot0 + nxt, grow, ix.row_stride);
+#pragma unroll
+            for (int r = 0; r < ROW_GROUP; ++r)
+                if (has && rank == r0 + r) mine = finish_f32(ix.metric, raw[r], c.qn, in);
+            slot0 += ROW_GROUP;
+            if (slot0 >= S) slot0 = 0;
+        }
+    } else if (KIND == KIND_F32_LANE) {
         if (mask >> lane & 1) {
             const float* row = reinterpret_cast<const float*>(ix.rows + (size_t)s * ix.row_stride);
             float in = (ix.metric == HB_COSINE) ? __ldg(&ix.hdr[s]) : 0.0f;
@@ -174,18 +231,21 @@ enum ChunkMode { CH_EP, CH_NBR, CH_LINEAR };
 // One chunk of <= 32 points (lane i holds the i-th, ascending).  Mirrors, for all 32 at once, the body of
 // `for &ep in eps` (reader.rs:315-325), `for point in links.iter()` (reader.rs:342-366) or the
 // brute-force loop (reader.rs:683-705).
-template <int MODE>
+template <int KIND, int MODE>
 __device__ __forceinline__ void process_chunk(Ctx& c, uint32_t s, bool valid, float f_max, int ef, bool filt, int lvl01) {
     const int lane = lane_id();
     bool live;
+    PH_DECL
     if (MODE == CH_NBR) live = vis_test_and_set(c, s, valid);           // `if !path.insert(point) { continue }`
     else if (MODE == CH_EP) { vis_test_and_set(c, s, valid); live = valid; }  // path.insert(ep), result ignored
     else live = valid;
     unsigned lm = __ballot_sync(FULL, live);
+    if (lvl01) PH_ADD(c, PH_VIS)
     if (!lm) return;
-    c.n_dist[lvl01] += __popc(lm);
-    float dist = chunk_distances(c, lm, s);
+    c.cur_dist += __popc(lm);
+    float dist = chunk_distances<KIND>(c, lm, s);
     uint32_t bits = __float_as_uint(dist);
+    if (lvl01) PH_ADD(c, PH_ROWS)
     if (MODE != CH_LINEAR && c.p.pass == 0 && __ballot_sync(FULL, live && (bits >> 31))) { c.overflow = true; return; }
     bool pf = live && passes_filter(c, s, filt);
     bool acc;
@@ -213,26 +273,31 @@ __device__ __forceinline__ void process_chunk(Ctx& c, uint32_t s, bool valid, fl
         uint32_t b = __shfl_sync(FULL, bits, src), sl = __shfl_sync(FULL, s, src);
         queue_push(c, b, sl, ef);
     }
+    if (lvl01) PH_ADD(c, PH_HEAP)
 }
 
 // Visitor::visit — reader.rs:301-369.  Entry points: `eps` (n_eps slots in global memory) or `single`.
-__device__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_eps, uint32_t single, uint32_t level, int ef, bool filt) {
+template <int KIND>
+__device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_eps, uint32_t single, uint32_t level, int ef, bool filt) {
     const DevIndex& ix = c.p.ix;
     const int lane = lane_id();
     const int l01 = level ? 0 : 1;
     c.res_len = 0;
     c.q_len = 0;
+    c.cur_dist = c.cur_exp = c.cur_deg = 0;
     if (eps) {
         for (uint32_t base = 0; base < n_eps; base += 32) {
             bool valid = base + lane < n_eps;
             uint32_t s = valid ? __ldg(&eps[base + lane]) : 0;
-            process_chunk<CH_EP>(c, s, valid, FLT_MAX, ef, filt, l01);
+            process_chunk<KIND, CH_EP>(c, s, valid, FLT_MAX, ef, filt, l01);
         }
     } else {
-        process_chunk<CH_EP>(c, single, lane == 0, FLT_MAX, ef, filt, l01);
+        process_chunk<KIND, CH_EP>(c, single, lane == 0, FLT_MAX, ef, filt, l01);
     }
     const uint32_t* off = ix.off[level];
     const uint32_t* nbr = ix.nbr[level];
+    const uint32_t* nbrx = level == 0 ? ix.nbr0x : nullptr;
+    uint32_t spec_cs = 0xffffffffu, spec_adj = 0xffffffffu;  // adjacency line requested ahead of its pop
     while (c.q_len > 0 && !c.overflow) {
         u64 top = c.que[c.q_len - 1];
         float f = key_dist(top);
@@ -240,19 +305,38 @@ __device__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_eps, uint32_t sing
         if (f > f_max) break;
         c.q_len--;
         uint32_t cs = ~(uint32_t)top;
-        uint32_t b = __ldg(&off[cs]), e = __ldg(&off[cs + 1]);
-        c.n_exp[l01] += 1;
-        c.n_deg[l01] += e - b;
-        for (uint32_t base = b; base < e; base += 32) {
-            bool valid = base + lane < e;
-            uint32_t s = valid ? __ldg(&nbr[base + lane]) : 0;
-            process_chunk<CH_NBR>(c, s, valid, f_max, ef, filt, l01);
+        c.cur_exp += 1;
+        if (nbrx) {
+            PH_DECL
+            uint32_t s = (cs == spec_cs) ? spec_adj : __ldg(&nbrx[(size_t)cs * FIXED_DEG + lane]);
+            bool valid = s != 0xffffffffu;
+            c.cur_deg += __popc(__ballot_sync(FULL, valid));
+            PH_ADD(c, PH_ADJ)
+            // the entry now on top of the queue is popped next unless one of cs's neighbours beats it
+            if (c.q_len > 0) {
+                spec_cs = ~(uint32_t)c.que[c.q_len - 1];
+                spec_adj = __ldg(&nbrx[(size_t)spec_cs * FIXED_DEG + lane]);
+            } else {
+                spec_cs = 0xffffffffu;
+            }
+            process_chunk<KIND, CH_NBR>(c, valid ? s : 0, valid, f_max, ef, filt, l01);
+        } else {
+            uint32_t b = __ldg(&off[cs]), e = __ldg(&off[cs + 1]);
+            c.cur_deg += e - b;
+            for (uint32_t base = b; base < e; base += 32) {
+                bool valid = base + lane < e;
+                uint32_t s = valid ? __ldg(&nbr[base + lane]) : 0;
+                process_chunk<KIND, CH_NBR>(c, s, valid, f_max, ef, filt, l01);
+            }
         }
     }
+    if (level) { c.n_dist_up += c.cur_dist; c.n_exp_up += c.cur_exp; c.n_deg_up += c.cur_deg; }
+    else { c.n_dist_l0 += c.cur_dist; c.n_exp_l0 += c.cur_exp; c.n_deg_l0 += c.cur_deg; }
 }
 
 // ---- query staging ---------------------------------------------------------------------------------------
 // UnalignedVector::from_slice + D::new_header (reader.rs:140-141), into the device row layout.
+template <int KIND>
 __device__ void stage_query(Ctx& c, float* qs, uint64_t qi) {
     const DevIndex& ix = c.p.ix;
     const int lane = lane_id();
@@ -266,7 +350,7 @@ __device__ void stage_query(Ctx& c, float* qs, uint64_t qi) {
         for (uint32_t i = lane; i < words16; i += 32) q16[i] = make_uint4(0, 0, 0, 0);
         __syncwarp();
         const float* src = c.p.q + qi * ix.dims;
-        if (ix.kind == KIND_F32_WARP) {
+        if (KIND == KIND_F32_WARP) {
             uint32_t main = ix.dims - ix.tail;
             for (uint32_t e = lane; e < ix.dims; e += 32) {
                 float v = __ldg(src + e);
@@ -277,7 +361,7 @@ __device__ void stage_query(Ctx& c, float* qs, uint64_t qi) {
                     qs[ix.tail_off + (e - main)] = v;
                 }
             }
-        } else if (ix.kind == KIND_F32_LANE) {
+        } else if (KIND == KIND_F32_LANE) {
             for (uint32_t e = lane; e < ix.dims; e += 32) qs[e] = __ldg(src + e);
         } else {
             // src/unaligned_vector/binary.rs:80-94 (x > 0) and binary_quantized.rs:80-91 (sign positive)
@@ -299,7 +383,7 @@ __device__ void stage_query(Ctx& c, float* qs, uint64_t qi) {
     float qn = 0.0f;
     if (ix.metric == HB_COSINE) {
         float dot;
-        if (ix.kind == KIND_F32_WARP) {
+        if (KIND == KIND_F32_WARP) {
             // dot(q, q) in the same lane order: the query doubles as the "row" (shared-memory reads)
             float acc = 0.0f;
             const float4* q4 = reinterpret_cast<const float4*>(qs);
@@ -330,17 +414,39 @@ __device__ void sort_tail(u64* a, int first, int n) {
     }
 }
 
-__device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64* heap, float* qs) {
+// first item not yet in `path`, scanning forward from 32-word window `wb` (the cursor of reader.rs:772-783)
+__device__ __forceinline__ uint32_t next_unseen(const Ctx& c, uint32_t& wb) {
+    const uint32_t n = c.p.ix.n, n_words = (n + 31) >> 5;
+    for (; wb < n_words; wb += 32) {
+        uint32_t w = wb + lane_id();
+        uint32_t word = 0xffffffffu;
+        if (w < n_words) {
+            word = __ldcg(&c.vis[w]);
+            if (w == n_words - 1 && (n & 31)) word |= ~((1u << (n & 31)) - 1);
+        }
+        unsigned m = __ballot_sync(FULL, word != 0xffffffffu);
+        if (m) {
+            int src = __ffs(m) - 1;
+            uint32_t wsel = __shfl_sync(FULL, word, src);
+            return (wb + src) * 32 + (__ffs(~wsel) - 1);
+        }
+    }
+    return 0xffffffffu;
+}
+
+template <int KIND>
+__device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64* heap, float* qs, RowRing& ring) {
     const DevIndex& ix = p.ix;
     const int lane = lane_id();
-    Ctx c(p);
+    Ctx c(p, ring);
     c.res = heap; c.res_cap = p.res_cap; c.res_len = 0;
     c.que = heap + p.res_cap; c.q_cap = p.q_cap; c.q_len = 0;
     c.vis = p.visited + (size_t)slot_idx * p.vis_words;
     c.touched = p.touched + (size_t)slot_idx * p.touched_cap;
     c.touched_len = 0; c.touched_over = false;
     c.excl = 0xffffffffu; c.overflow = false;
-    c.n_dist[0] = c.n_dist[1] = c.n_exp[0] = c.n_exp[1] = c.n_deg[0] = c.n_deg[1] = 0;
+    c.n_dist_up = c.n_exp_up = c.n_deg_up = c.n_dist_l0 = c.n_exp_l0 = c.n_deg_l0 = 0;
+    c.cur_dist = c.cur_exp = c.cur_deg = 0;
     u64 flags = p.pass ? HB_FLAG_SLOW_PATH : 0;
     const uint32_t count = p.count;
     const int ef0 = (int)max(p.ef_raw, p.count);
@@ -349,7 +455,13 @@ __device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64*
         if (lane == 0) p.out_len[qi] = 0xffffffffu;
         return;
     }
-    stage_query(c, qs, qi);
+#ifdef HB_PHASES
+    for (int i = 0; i < PH_N; ++i) c.ph[i] = 0;
+    const long long ph_q0 = clock64();
+#endif
+    PH_DECL
+    stage_query<KIND>(c, qs, qi);
+    PH_ADD(c, PH_STAGE)
 
     int n_out = 0;
     if (p.mode >= 2) {
@@ -358,59 +470,73 @@ __device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64*
         for (uint32_t base = 0; base < p.n_cand_slots; base += 32) {
             bool valid = base + lane < p.n_cand_slots;
             uint32_t s = valid ? __ldg(&p.cand_slots[base + lane]) : 0;
-            process_chunk<CH_LINEAR>(c, s, valid, FLT_MAX, (int)count, false, 1);
+            process_chunk<KIND, CH_LINEAR>(c, s, valid, FLT_MAX, (int)count, false, 1);
         }
+        c.n_dist_l0 += c.cur_dist;
         n_out = c.res_len;
     } else {
-        uint32_t ep_single = 0;
+        // One call site of visit() drives the whole search as a small state machine:
+        //   ST_UPPER  greedy descent, ef = 1, levels max_level..1, shared visited set (reader.rs:732-741)
+        //   ST_L0     the ef-bounded layer-0 walk (reader.rs:743-767) / by_item's seeded walk (reader.rs:842-862)
+        //   ST_FB     exhaustive fallback, one visit per unseen item (reader.rs:771-795 / 865-889)
+        enum { ST_UPPER, ST_L0, ST_FB };
+        uint32_t ep_single = 0, level = 0;
         const uint32_t* eps = ix.eps;
+        int st = ST_L0;
         if (p.mode & 1) {  // nns_by_item — reader.rs:836-842
             c.excl = p.q_slots[qi];
             ep_single = c.excl;
             eps = nullptr;
-        } else {  // hnsw_search — reader.rs:732-743
-            for (uint32_t level = ix.max_level; level >= 1 && !c.overflow; --level) {
-                visit(c, eps, ix.n_ep, ep_single, level, 1, false);
-                if (c.res_len == 0) break;       // reference: expect("No neighbor was found")
-                ep_single = (uint32_t)c.res[0];  // peek_min
-                eps = nullptr;
-                __syncwarp();
-            }
-            vis_clear(c);
+        } else if (ix.max_level >= 1) {
+            st = ST_UPPER;
+            level = ix.max_level;
         }
-        if (!c.overflow) visit(c, eps, ix.n_ep, ep_single, 0, ef0, true);
-        int acc_len = c.res_len;
-        if (!c.overflow && acc_len < (int)count) {
-            // exhaustive fallback over unseen items — reader.rs:771-795 / 865-889
-            flags |= HB_FLAG_FALLBACK;
-            const int target = (p.mode & 1) ? (int)count : (int)p.ef_raw;
-            const int first = acc_len;
-            u64* base_res = c.res;
-            const int base_cap = c.res_cap;
-            bool done = false;
-            for (uint32_t wb = 0; wb < p.vis_words && !done && !c.overflow; wb += 32) {
-                for (;;) {
-                    uint32_t w = wb + lane;
-                    uint32_t word = 0xffffffffu;
-                    if (w < p.vis_words) {
-                        word = __ldcg(&c.vis[w]);
-                        if (w == p.vis_words - 1 && (ix.n & 31)) word |= ~((1u << (ix.n & 31)) - 1);
-                    }
-                    unsigned m = __ballot_sync(FULL, word != 0xffffffffu);
-                    if (!m) break;
-                    int src = __ffs(m) - 1;
-                    uint32_t wsel = __shfl_sync(FULL, word, src);
-                    uint32_t s = (wb + src) * 32 + (__ffs(~wsel) - 1);
-                    int ef2 = (p.mode & 1) ? (int)count - acc_len : max(0, (int)p.ef_raw - acc_len);
-                    c.res = base_res + acc_len;
-                    c.res_cap = base_cap - acc_len;
-                    visit(c, nullptr, 0, s, 0, ef2, true);
-                    acc_len += c.res_len;
-                    __threadfence_block();
-                    if (acc_len >= target || c.overflow) { done = true; break; }
+        const int target = (p.mode & 1) ? (int)count : (int)p.ef_raw;
+        u64* const base_res = c.res;
+        const int base_cap = c.res_cap;
+        int acc_len = 0, first = -1, ef = 0;
+        uint32_t wb = 0;
+        for (;;) {
+            bool filt = true;
+            if (st == ST_UPPER) { ef = 1; filt = false; }
+            else if (st == ST_L0) { ef = ef0; level = 0; }
+            visit<KIND>(c, eps, ix.n_ep, ep_single, level, ef, filt);
+            if (c.overflow) break;
+            if (st == ST_UPPER) {
+                bool found = c.res_len != 0;       // reference: expect("No neighbor was found")
+                if (found) { ep_single = (uint32_t)c.res[0]; eps = nullptr; }  // peek_min
+                __syncwarp();
+                --level;
+                if (level == 0 || !found) {
+                    vis_clear(c);                  // path.clear(), reader.rs:743
+                    PH_ADD(c, PH_UPPER)
+                    st = ST_L0;
                 }
+                continue;
             }
-            c.res = base_res; c.res_cap = base_cap; c.res_len = acc_len;
+            if (st == ST_L0) {
+                PH_RESET
+                acc_len = c.res_len;
+                if (acc_len >= (int)count) break;
+                flags |= HB_FLAG_FALLBACK;
+                first = acc_len;
+                st = ST_FB;
+            } else {
+                acc_len += c.res_len;
+                __threadfence_block();
+                if (acc_len >= target) break;
+            }
+            uint32_t s = next_unseen(c, wb);
+            if (s == 0xffffffffu) break;
+            ep_single = s;
+            eps = nullptr;
+            ef = (p.mode & 1) ? (int)count - acc_len : max(0, (int)p.ef_raw - acc_len);
+            c.res = base_res + acc_len;
+            c.res_cap = base_cap - acc_len;
+        }
+        c.res = base_res; c.res_cap = base_cap;
+        if (first >= 0) {
+            c.res_len = acc_len;
             if (!c.overflow) sort_tail(c.res, first, acc_len);
         }
         n_out = min(c.res_len, (int)count);
@@ -437,31 +563,50 @@ __device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64*
         p.out_len[qi] = (uint32_t)n_out;
         if (p.out_ctr) {
             uint64_t* o = p.out_ctr + qi * HB_N_CTR;
-            o[HB_CTR_DIST_UPPER] = c.n_dist[0]; o[HB_CTR_DIST_L0] = c.n_dist[1];
-            o[HB_CTR_EXP_UPPER] = c.n_exp[0]; o[HB_CTR_EXP_L0] = c.n_exp[1];
-            o[HB_CTR_DEG_UPPER] = c.n_deg[0]; o[HB_CTR_DEG_L0] = c.n_deg[1];
+            o[HB_CTR_DIST_UPPER] = c.n_dist_up; o[HB_CTR_DIST_L0] = c.n_dist_l0;
+            o[HB_CTR_EXP_UPPER] = c.n_exp_up; o[HB_CTR_EXP_L0] = c.n_exp_l0;
+            o[HB_CTR_DEG_UPPER] = c.n_deg_up; o[HB_CTR_DEG_L0] = c.n_deg_l0;
             o[HB_CTR_FLAGS] = flags; o[HB_CTR_RESERVED] = 0;
         }
     }
     __syncwarp();
+#ifdef HB_PHASES
+    PH_ADD(c, PH_TAIL)
+    c.ph[PH_TOTAL] = clock64() - ph_q0;
+    if (lane == 0)
+        for (int i = 0; i < PH_N; ++i) atomicAdd(&g_phase[i], (unsigned long long)c.ph[i]);
+#endif
 }
 
-__global__ void __launch_bounds__(128) hnsw_search_kernel(const __grid_constant__ SearchParams p) {
-    extern __shared__ __align__(16) unsigned char smem[];
+// Shared memory of one warp: [row ring][ring barriers][query][heaps (pass 0 only)].
+template <int KIND>
+__global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, KIND == KIND_F32_WARP ? 3 : 4) hnsw_search_kernel(const __grid_constant__ SearchParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
     const int warp_in_block = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
     const int slot_idx = blockIdx.x * warps_per_block + warp_in_block;
-    const size_t heap_bytes = (size_t)(p.res_cap + p.q_cap) * 8;
-    u64* heap;
-    float* qs;
-    if (p.pass == 0) {
-        size_t per_warp = (heap_bytes + p.q_smem_bytes + 15) & ~(size_t)15;
-        unsigned char* base = smem + per_warp * warp_in_block;
-        qs = reinterpret_cast<float*>(base);
-        heap = reinterpret_cast<u64*>(base + p.q_smem_bytes);
-    } else {
-        qs = reinterpret_cast<float*>(smem + (size_t)p.q_smem_bytes * warp_in_block);
-        heap = p.gheap + (size_t)slot_idx * (p.res_cap + p.q_cap);
+    const size_t ring_bytes = (size_t)p.ring_slots * p.ring_stride;
+    const size_t bar_bytes = ((size_t)p.ring_slots * 8 + 15) & ~(size_t)15;
+    const size_t heap_bytes = p.pass == 0 ? (size_t)(p.res_cap + p.q_cap) * 8 : 0;
+    const size_t per_warp = (ring_bytes + bar_bytes + p.q_smem_bytes + heap_bytes + 127) & ~(size_t)127;
+    unsigned char* base = smem + per_warp * warp_in_block;
+    float* qs = reinterpret_cast<float*>(base + ring_bytes + bar_bytes);
+    u64* heap = p.pass == 0 ? reinterpret_cast<u64*>(base + ring_bytes + bar_bytes + p.q_smem_bytes)
+                            : p.gheap + (size_t)slot_idx * (p.res_cap + p.q_cap);
+    RowRing ring;
+    ring.ptr = base;
+    ring.data = smem_addr(base);
+    ring.bars = smem_addr(base + ring_bytes);
+    ring.slots = p.ring_slots;
+    ring.stride = p.ring_stride;
+    ring.phase = 0;
+    ring.policy = l2_policy_evict_first();
+    if (p.ring_slots) {
+        if (lane_id() == 0) {
+            for (uint32_t i = 0; i < p.ring_slots; ++i) mbar_init(ring.bars + i * 8, 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
     }
     const uint32_t n_work = p.pass == 0 ? p.n_work : *p.n_overflow;
     for (;;) {
@@ -470,11 +615,18 @@ __global__ void __launch_bounds__(128) hnsw_search_kernel(const __grid_constant_
         w = __shfl_sync(FULL, w, 0);
         if (w >= n_work) break;
         uint64_t qi = p.pass == 0 ? w : p.overflow_list[w];
-        run_query(p, qi, slot_idx, heap, qs);
+        run_query<KIND>(p, qi, slot_idx, heap, qs, ring);
     }
 }
 
 unsigned long long g_launches = 0;
+
+// dev: read and reset the phase timers (all zero unless built with -DHB_PHASES)
+void read_phases(unsigned long long* out) {
+    cudaMemcpyFromSymbol(out, g_phase, sizeof(unsigned long long) * PH_N);
+    unsigned long long z[16] = {};
+    cudaMemcpyToSymbol(g_phase, z, sizeof(z));
+}
 
 __global__ void fill_iota_kernel(uint32_t* list, uint32_t* n_out, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -483,7 +635,39 @@ __global__ void fill_iota_kernel(uint32_t* list, uint32_t* n_out, uint32_t n) {
 }
 
 size_t search_smem_per_warp(const SearchParams& p) {
-    return ((size_t)(p.res_cap + p.q_cap) * 8 + p.q_smem_bytes + 15) & ~(size_t)15;
+    size_t ring_bytes = (size_t)p.ring_slots * p.ring_stride;
+    size_t bar_bytes = ((size_t)p.ring_slots * 8 + 15) & ~(size_t)15;
+    size_t heap_bytes = p.pass == 0 ? (size_t)(p.res_cap + p.q_cap) * 8 : 0;
+    return (ring_bytes + bar_bytes + p.q_smem_bytes + heap_bytes + 127) & ~(size_t)127;
+}
+
+typedef void (*search_kernel_t)(const SearchParams);
+static search_kernel_t kernel_for(int kind) {
+    switch (kind) {
+        case KIND_F32_WARP: return hnsw_search_kernel<KIND_F32_WARP>;
+        case KIND_F32_LANE: return hnsw_search_kernel<KIND_F32_LANE>;
+        default: return hnsw_search_kernel<KIND_BIN>;
+    }
+}
+static void set_kernel_attrs() {
+    static bool attr_set = false;
+    if (!attr_set) {
+        for (int k = 0; k < 3; ++k)
+            cudaFuncSetAttribute(kernel_for(k), cudaFuncAttributeMaxDynamicSharedMemorySize, SEARCH_MAX_SMEM);
+        attr_set = true;
+    }
+}
+
+int search_blocks_per_sm(const SearchParams& p) {
+    set_kernel_attrs();
+    int nb = 0;
+    size_t smem = search_smem_per_warp(p) * SEARCH_WARPS_PER_BLOCK;
+    if (smem > (size_t)SEARCH_MAX_SMEM) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel_for(p.ix.kind), SEARCH_WARPS_PER_BLOCK * 32, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return nb;
 }
 
 // Launch pass 0 (shared-memory heaps, `fast`) then pass 1 (global-memory heaps over the overflow list,
@@ -491,11 +675,7 @@ size_t search_smem_per_warp(const SearchParams& p) {
 hb_status launch_search(const SearchParams& fast, const SearchParams& slow, int blocks_fast, int blocks_slow, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     const int wpb = SEARCH_WARPS_PER_BLOCK;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(hnsw_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEARCH_MAX_SMEM);
-        attr_set = true;
-    }
+    set_kernel_attrs();
     cudaMemsetAsync(fast.work_counter, 0, 2 * sizeof(unsigned long long), stream);
     if (fast.res_cap) {
         cudaMemsetAsync(fast.n_overflow, 0, sizeof(uint32_t), stream);
@@ -503,15 +683,15 @@ hb_status launch_search(const SearchParams& fast, const SearchParams& slow, int 
         uint64_t need = ((uint64_t)fast.n_work + wpb - 1) / wpb;
         int blocks = (uint64_t)blocks_fast > need ? (int)need : blocks_fast;
         if (blocks < 1) blocks = 1;
-        hnsw_search_kernel<<<blocks, wpb * 32, smem, stream>>>(fast);
+        kernel_for(fast.ix.kind)<<<blocks, wpb * 32, smem, stream>>>(fast);
         ++g_launches;
     } else {
         uint32_t n = fast.n_work;
         fill_iota_kernel<<<(n + 255) / 256, 256, 0, stream>>>(fast.overflow_list, fast.n_overflow, n);
         ++g_launches;
     }
-    size_t smem = (size_t)slow.q_smem_bytes * wpb;
-    hnsw_search_kernel<<<blocks_slow, wpb * 32, smem, stream>>>(slow);
+    size_t smem = search_smem_per_warp(slow) * wpb;
+    kernel_for(slow.ix.kind)<<<blocks_slow, wpb * 32, smem, stream>>>(slow);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("search launch failed: %s", cudaGetErrorString(e)); return HB_ECUDA; }

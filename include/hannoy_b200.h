@@ -143,6 +143,17 @@ hb_status hb_merge_topk_device(int device, const uint32_t* d_ids, const float* d
 /* number of kernel launches issued by this library in this process (for bench gpu_launches) */
 uint64_t hb_launch_count(void);
 
+/* Engine tuning knob (no reference counterpart; never changes results): e.g. "ring_bytes" (shared-memory
+ * bytes of rows in flight per query warp), "blocks_per_sm", "fixed_adjacency", "touched_cap".  Takes
+ * effect for indexes finalized / workspaces created afterwards; the environment variable HB_<KEY> is the
+ * default. */
+hb_status hb_tune(const char* key, int value);
+
+/* Development aid: cycles per phase of the search kernel summed over all queries since the last call
+ * (stage, upper layers, adjacency wait, visited filter, row gather+distance, heap update, tail, total).
+ * All zero unless the library was built with -DHB_PHASES. */
+void hb_debug_phases(uint64_t* out8);
+
 const char* hb_last_error(void);
 
 #ifdef __cplusplus

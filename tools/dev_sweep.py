@@ -1,0 +1,112 @@
+#!/usr/bin/env python
+"""Dev tool (GPU box): time the search kernel alone on one workload under several tunable settings, check
+parity against the oracle once, and (with HB_LIB_VARIANT=phases) print the per-phase cycle breakdown.
+
+  python tools/dev_sweep.py --workload c3 --ef 128 --sweep "ring_bytes=12288,24576;blocks_per_sm=2,3"
+"""
+import argparse
+import itertools
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="c3")
+    ap.add_argument("--n-items", type=int, default=0)
+    ap.add_argument("--ef", type=int, default=128)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--sweep", default="")
+    ap.add_argument("--parity", type=int, default=256)
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    import torch
+    import hannoy_b200 as hb
+    from hannoy_b200 import _lib
+    L = _lib.lib()
+    w = dict(bench.WORKLOADS[args.workload])
+    if args.n_items:
+        w["n"] = args.n_items
+    dev = torch.device("cuda", 0)
+    threads = len(os.sched_getaffinity(0))
+    log = lambda m: print(f"[sweep] {m}", file=sys.stderr, flush=True)
+    x = bench.gen_vectors(w["gen"], w["n"], w["dims"], w["seed"], dev)
+    q = bench.gen_vectors(w["gen"], w["nq"], w["dims"], w["seed"] + 1, dev)
+    x_host, q_host = x.cpu().numpy(), q.cpu().numpy()
+    del x
+    db = bench.build_or_load_graph(w, x_host, dev.type, threads, log)
+    rd = hb.Reader.from_arrays(w["metric"], w["dims"], db.ids(), db.rows(), db.headers(), db.layers(), db.entry_points,
+                               db.max_level, device=0)
+    k, nq = w["k"], w["nq"]
+    ef_raw = max(args.ef, k)
+    dq = q.contiguous()
+    d_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    d_dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    d_len = torch.empty((nq,), dtype=torch.int32, device=dev)
+    d_ctr = torch.zeros((nq, 8), dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step(ctr=False):
+        rd.search_device(dq.data_ptr(), nq, k, ef_raw, d_ids.data_ptr(), d_dist.data_ptr(), d_len.data_ptr(),
+                         d_ctr.data_ptr() if ctr else None, stream.cuda_stream)
+
+    keys, vals = [], []
+    for part in filter(None, args.sweep.split(";")):
+        kname, vs = part.split("=")
+        keys.append(kname)
+        vals.append([int(v) for v in vs.split(",")])
+    combos = list(itertools.product(*vals)) if keys else [()]
+    want = None
+    results = []
+    for combo in combos:
+        for kname, v in zip(keys, combo):
+            L.hb_tune(kname.encode(), v)
+        step(ctr=True)
+        torch.cuda.synchronize()
+        ctr = d_ctr.cpu().numpy().astype(np.uint64)
+        alg, vec = bench.algorithmic_bytes(ctr, w)
+        n_par = min(args.parity, nq)
+        if want is None:
+            want = db.search_by_vector(q_host[:n_par], k, ef=ef_raw, n_threads=threads, counters=True)
+        ids = d_ids[:n_par].cpu().numpy().view(np.uint32)
+        dd = d_dist[:n_par].cpu().numpy()
+        ln = d_len[:n_par].cpu().numpy().view(np.uint32)
+        ok = bool(np.array_equal(ln, want[2]) and np.array_equal(ids, want[0]) and np.array_equal(dd.view(np.uint32), want[1].view(np.uint32)))
+        ok_ctr = bool(np.array_equal(ctr[:n_par, :6], want[3][:n_par, :6].astype(np.uint64))) if len(want) > 3 else None
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        ph0 = np.zeros(8, np.uint64)
+        L.hb_debug_phases(ph0.ctypes.data)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        ph = np.zeros(8, np.uint64)
+        L.hb_debug_phases(ph.ctypes.data)
+        r = dict(tune=dict(zip(keys, combo)), ms=round(ms, 3), qps=round(nq / ms * 1e3), gbs=round(alg / ms / 1e6, 1), parity=ok, counters=ok_ctr,
+                 slow=int((ctr[:, 6] & 4).astype(bool).sum()), evals_per_q=float(ctr[:, :2].sum() / nq), exp_per_q=float(ctr[:, 2:4].sum() / nq))
+        if ph.sum():
+            tot = float(ph[7]) or 1.0
+            names = ["stage", "upper", "adj", "vis", "rows", "heap", "tail", "total"]
+            r["phase_frac"] = {n: round(float(p) / tot, 3) for n, p in zip(names, ph)}
+            r["cycles_per_query"] = round(tot / (nq * args.steps))
+        results.append(r)
+        print(json.dumps(r), flush=True)
+    if args.out:
+        json.dump(results, open(args.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
