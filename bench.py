@@ -170,6 +170,34 @@ def recall_at_k(ids, lens, gt, k):
     return hit / (len(ids) * k)
 
 
+def cpu_ground_truth(w, db, x_host, q, k, threads):
+    """Exact top-k ids on the host for the reference arm's recall rule (no GPU code involved): blocked sgemm for
+    the f32 metrics, the oracle's popcount scan for the binary ones."""
+    if w["metric"] not in ("euclidean", "cosine"):
+        return db.exact_knn(q, k, n_threads=threads)[0]
+    import torch
+    torch.set_num_threads(threads)
+    tq = torch.from_numpy(np.ascontiguousarray(q))
+    best_s = torch.full((len(q), k), -float("inf"))
+    best_i = torch.zeros((len(q), k), dtype=torch.int64)
+    chunk = 50_000
+    for s in range(0, len(x_host), chunk):
+        xb = torch.from_numpy(x_host[s:s + chunk])
+        dots = tq @ xb.T
+        if w["metric"] == "cosine":
+            score = dots / xb.norm(dim=1).clamp_min(1e-30)       # the query norm is constant per row: same ranking
+        else:
+            score = 2 * dots - xb.pow(2).sum(1)                   # -(|x|^2 - 2 q.x): same ranking as squared L2
+        ts, ti = score.topk(min(k, score.shape[1]), dim=1)
+        cat_s, cat_i = torch.cat([best_s, ts], 1), torch.cat([best_i, ti + s], 1)
+        best_s, sel = cat_s.topk(k, dim=1)
+        best_i = cat_i.gather(1, sel)
+    return best_i.numpy().astype(np.uint32)
+
+
+N_GT = 2000  # queries the recall rule is evaluated on (both arms, same queries)
+
+
 def algorithmic_bytes(ctr, w):
     """sum over layers of n_dist_evals*(row_bytes+hdr_bytes) + n_expansions*8 + 4*sum(deg)."""
     binary = w["metric"] not in ("euclidean", "cosine", "manhattan")
@@ -241,7 +269,7 @@ def main():
               "builder": "oracle restatement of hannoy Writer (reference Writer is Rust, not buildable here)"}
 
     if args.impl == "reference":
-        return run_reference(args, w, db, q_host, threads, config, log)
+        return run_reference(args, w, db, x_host, q_host, threads, config, log)
 
     import hannoy_b200 as hb
     t0 = time.time()
@@ -253,7 +281,7 @@ def main():
 
     # ---- pick ef: smallest with recall@k >= target against the exact k-NN kernel ----
     t0 = time.time()
-    n_gt = min(nq, 2000)
+    n_gt = min(nq, N_GT)
     gt, _ = hb.exact_knn(rd, q_host[:n_gt], k)
     log(f"exact k-NN ground truth for {n_gt} queries in {time.time() - t0:.1f}s")
     sweep = {}
@@ -354,6 +382,13 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = alg_bytes / (ms_per_step / 1e3) / 1e9
+        traffic, traffic_src = None, None
+        try:  # measured DRAM bytes per launch from the committed ncu capture of this workload, if there is one
+            t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+            if t and t["ef_search"] == ef_pick and not args.n_items:
+                traffic, traffic_src = int(t["dram_bytes_per_launch"]), t["source"]
+        except Exception:
+            pass
         # ---- CPU baseline: the oracle port on all host threads, bounded sample ----
         n_cpu = min(nq, 2000)
         t0 = time.perf_counter()
@@ -369,7 +404,7 @@ def main():
             "e2e": {"value": round(e2e_qps, 1), "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                          "algorithmic_bytes_per_step": int(alg_bytes), "gathered_vector_bytes_per_step": int(vec_bytes),
                          "kernel": "hnsw_search_kernel", "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)},
             "cpu_baseline": {"value": round(n_cpu / t_cpu, 1), "unit": "queries/s", "cores": threads, "kind": "port",
@@ -382,18 +417,23 @@ def main():
     return 0
 
 
-def run_reference(args, w, db, q_host, threads, config, log):
+def run_reference(args, w, db, x_host, q_host, threads, config, log):
     """Reference arm: the reference's CPU search (oracle port; the Rust crate cannot be built here)."""
     k = w["k"]
     ef = args.ef or int(os.environ.get("HB_REF_EF", 0))
+    sweep = {}
     if not ef:
-        # same ef rule as our arm, evaluated with the oracle's own exact k-NN on a small sample
-        n_gt = 200
-        gt, _ = db.exact_knn(q_host[:n_gt], k, n_threads=threads)
+        # same ef rule as our arm, on the same N_GT queries, with a host-side exact ground truth
+        n_gt = min(w["nq"], N_GT)
+        t0 = time.time()
+        gt = cpu_ground_truth(w, db, x_host, q_host[:n_gt], k, threads)
+        log(f"host exact k-NN ground truth for {n_gt} queries in {time.time() - t0:.1f}s")
         for ef in w["efs"]:
             ids, dd, lens, _ = db.search_by_vector(q_host[:n_gt], k, ef=max(ef, k), n_threads=threads)
-            if recall_at_k(ids, lens, gt, k) >= RECALL_TARGET:
+            sweep[ef] = round(recall_at_k(ids, lens, gt, k), 4)
+            if sweep[ef] >= RECALL_TARGET:
                 break
+        log(f"recall sweep {sweep} -> ef_search={ef}")
     ef_raw = max(ef, k)
     n_s = min(w["nq"], 2000)
     for _ in range(max(args.warmup, 1)):
@@ -406,7 +446,7 @@ def run_reference(args, w, db, q_host, threads, config, log):
     line = {
         "impl": "reference", "metric": "QPS at recall@10>=0.95 (batched)", "value": round(qps, 1), "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(config, ef_search=ef),
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(config, ef_search=ef, recall_sweep=sweep),
         "cpu_baseline": {"value": round(qps, 1), "unit": "queries/s", "cores": threads, "kind": "port",
                          "sample": f"{n_s} queries per step, oracle port on {threads} threads"},
         "e2e": {"value": round(qps, 1), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
