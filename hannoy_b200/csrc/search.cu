@@ -227,6 +227,7 @@ __device__ __forceinline__ float chunk_distances(Ctx& c, unsigned mask, uint32_t
 }
 
 enum ChunkMode { CH_EP, CH_NBR, CH_LINEAR };
+constexpr int MERGE_TILES = 8;  // heaps of up to 256 entries are updated by one merge pass per chunk
 
 // One chunk of <= 32 points (lane i holds the i-th, ascending).  Mirrors, for all 32 at once, the body of
 // `for &ep in eps` (reader.rs:315-325), `for point in links.iter()` (reader.rs:342-366) or the
@@ -262,16 +263,43 @@ __device__ __forceinline__ void process_chunk(Ctx& c, uint32_t s, bool valid, fl
     unsigned accm = __ballot_sync(FULL, acc);
     unsigned resm = __ballot_sync(FULL, acc && pf);
     u64 key = ((u64)bits << 32) | s;
-    for (unsigned m = resm; m; m &= m - 1) {
-        u64 k = __shfl_sync(FULL, key, __ffs(m) - 1);
-        if (MODE == CH_EP) res_push(c, k);       // reader.rs:322-324: unconditional
-        else res_accept(c, k, ef);
-    }
-    if (MODE == CH_LINEAR) return;
-    for (unsigned m = accm; m; m &= m - 1) {
-        int src = __ffs(m) - 1;
-        uint32_t b = __shfl_sync(FULL, bits, src), sl = __shfl_sync(FULL, s, src);
-        queue_push(c, b, sl, ef);
+    if (c.res_len <= 32 * MERGE_TILES && c.q_len <= 32 * MERGE_TILES) {
+        // All accepted points of the chunk enter the heaps in one merge pass each (sorted.cuh merge_batch).
+        // Result set: pushing the keys one by one with `if len == ef { push_pop_max } else { push }` leaves the
+        // min(ef, len + m) smallest of the union when len <= ef, and the whole union when len > ef (or for entry points).
+        const int m_res = __popc(resm);
+        int target = (MODE == CH_EP || c.res_len > ef) ? c.res_len + m_res : min(ef, c.res_len + m_res);
+        if (target > c.res_cap) { c.overflow = true; return; }
+        if (m_res) c.res_len = merge_batch<false, false, MERGE_TILES>(c.res, c.res_len, acc && pf, key, target, 0u, nullptr);
+        if (MODE == CH_LINEAR) return;
+        // Queue: entries that can never be popped (is_dead, judged against the UPDATED result set) are not pushed,
+        // and old ones — they sit at the front of the descending array — are trimmed in the same pass.
+        const bool prune = c.p.pass == 0 && c.res_len >= ef && c.res_len > 0 && !(c.res[c.res_len - 1] >> 63);
+        const uint32_t mb = prune ? (uint32_t)(c.res[c.res_len - 1] >> 32) : 0xffffffffu;
+        const bool qhas = acc && !(prune && !(bits >> 31) && bits > mb);
+        const int mq = __popc(__ballot_sync(FULL, qhas));
+        if (c.q_len + mq > c.q_cap) {
+            int d0 = 0;
+            if (prune) {
+                for (int i = lane; i < c.q_len; i += 32) d0 += (uint32_t)(c.que[i] >> 32) > mb;
+                d0 = __reduce_add_sync(FULL, d0);
+            }
+            if (c.q_len + mq - d0 > c.q_cap) { c.overflow = true; return; }  // would have to drop a live entry
+        }
+        if (mq || prune)
+            c.q_len = merge_batch<true, true, MERGE_TILES>(c.que, c.q_len, qhas, ((u64)bits << 32) | (uint32_t)(~s), c.q_cap, mb, nullptr);
+    } else {
+        for (unsigned m = resm; m; m &= m - 1) {
+            u64 k = __shfl_sync(FULL, key, __ffs(m) - 1);
+            if (MODE == CH_EP) res_push(c, k);       // reader.rs:322-324: unconditional
+            else res_accept(c, k, ef);
+        }
+        if (MODE == CH_LINEAR) return;
+        for (unsigned m = accm; m; m &= m - 1) {
+            int src = __ffs(m) - 1;
+            uint32_t b = __shfl_sync(FULL, bits, src), sl = __shfl_sync(FULL, s, src);
+            queue_push(c, b, sl, ef);
+        }
     }
     if (lvl01) PH_ADD(c, PH_HEAP)
 }

@@ -64,4 +64,65 @@ __device__ __forceinline__ void topk_insert(u64* a, int& len, int cap, u64 key) 
     }
 }
 
+// ---- batched merge -------------------------------------------------------------------------------------
+// Merge up to 32 new keys (lane L contributes `key` iff `has`) into the sorted array a[0..len) in ONE pass:
+// every lane binary-searches the slot of its own key, the old entries are pulled into registers, each
+// entry's displacement is the number of new keys that sort before it, then everything is written back.
+// Equivalent to inserting the keys one after the other (all keys are distinct), at the cost of one insertion.
+//   DESC       array is descending (search queue, next pop at the end) instead of ascending (result set)
+//   drop_above (TRIM only) old entries whose distance bits exceed it are dropped: they sit at the front of a
+//              descending array
+//   keep       final length is capped to `keep` (the entries that sort last are dropped)
+// Needs len <= 32 * MAX_TILES.  Returns the new length; *n_trimmed = entries dropped at the front.
+template <bool DESC, bool TRIM, int MAX_TILES>
+__device__ __forceinline__ int merge_batch(u64* a, int len, bool has, u64 key, int keep, uint32_t drop_above, int* n_trimmed) {
+    const int lane = lane_id();
+    const unsigned hm = __ballot_sync(FULL, has);
+    int pos = 0;
+    if (has) {
+        int lo = 0, hi = len;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            u64 x = a[mid];
+            bool before = DESC ? (x > key) : (x < key);
+            if (before) lo = mid + 1; else hi = mid;
+        }
+        pos = lo;
+    }
+    u64 v[MAX_TILES];
+    int sh[MAX_TILES];
+    int d = 0;
+#pragma unroll
+    for (int t = 0; t < MAX_TILES; ++t) {
+        int i = t * 32 + lane;
+        v[t] = (i < len) ? a[i] : 0ull;
+        sh[t] = 0;
+        if (TRIM) d += __popc(__ballot_sync(FULL, i < len && (uint32_t)(v[t] >> 32) > drop_above));
+    }
+    int rank = 0;
+    for (unsigned m = hm; m; m &= m - 1) {
+        int src = __ffs(m) - 1;
+        u64 kb = __shfl_sync(FULL, key, src);
+        int pb = __shfl_sync(FULL, pos, src);
+        rank += DESC ? (kb > key) : (kb < key);
+#pragma unroll
+        for (int t = 0; t < MAX_TILES; ++t) sh[t] += (pb <= t * 32 + lane);
+    }
+    __syncwarp();
+    const int new_len = min(len + __popc(hm) - d, keep);
+#pragma unroll
+    for (int t = 0; t < MAX_TILES; ++t) {
+        int i = t * 32 + lane;
+        int j = i + sh[t] - d;
+        if (i < len && j >= 0 && j < new_len) a[j] = v[t];
+    }
+    if (has) {
+        int j = pos + rank - d;
+        if (j >= 0 && j < new_len) a[j] = key;
+    }
+    __syncwarp();
+    if (n_trimmed) *n_trimmed = d;
+    return new_len;
+}
+
 }  // namespace hb
