@@ -22,7 +22,7 @@ EXPORTS = [
     "hb_index_finalize", "hb_index_free", "hb_index_dimensions", "hb_index_n_items", "hb_index_n_entry_points",
     "hb_index_max_level", "hb_index_version", "hb_index_item_ids", "hb_index_contains_item", "hb_index_item_vector",
     "hb_search_by_vector", "hb_search_by_item", "hb_search_by_vector_device", "hb_exact_knn", "hb_merge_topk_device",
-    "hb_launch_count", "hb_last_error", "hb_tune", "hb_debug_phases",
+    "hb_launch_count", "hb_last_error", "hb_tune", "hb_debug_phases", "hb_debug_trace",
 ]
 
 
@@ -61,7 +61,7 @@ def lib():
         "hb_search_by_vector_device": (i32, [vp, vp, u64, u32, u32, vp, vp, vp, vp, vp]),
         "hb_exact_knn": (i32, [vp, vp, u64, u32, u32, vp, vp]),
         "hb_merge_topk_device": (i32, [i32, vp, vp, u32, u64, u32, vp, vp, vp, vp]),
-        "hb_tune": (i32, [C.c_char_p, i32]), "hb_debug_phases": (None, [vp]), "hb_launch_count": (u64, []), "hb_last_error": (C.c_char_p, []),
+        "hb_tune": (i32, [C.c_char_p, i32]), "hb_debug_phases": (None, [vp]), "hb_debug_trace": (u32, [vp, u32]), "hb_launch_count": (u64, []), "hb_last_error": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -85,7 +85,10 @@ struct SearchParams {
     uint32_t ring_slots = 0;           // KIND_F32_WARP: rows in flight per warp (multiple of ROW_GROUP), ring.cuh
     uint32_t ring_stride = 0;          // bytes between ring slots
 };
-constexpr int ROW_GROUP = 4;           // rows reduced together by one warp
+#ifndef HB_ROW_GROUP
+#define HB_ROW_GROUP 4
+#endif
+constexpr int ROW_GROUP = HB_ROW_GROUP;  // rows reduced together by one warp
 
 // ---- host-side snapshot -----------------------------------------------------------------------
 struct HostLayer {
@@ -174,4 +177,5 @@ hb_status launch_merge_topk(const uint32_t* d_ids, const float* d_dist, uint32_t
                             uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len, void* stream);
 extern unsigned long long g_launches;
 void read_phases(unsigned long long* out);
+uint32_t read_trace(unsigned long long* out, uint32_t cap);
 }  // namespace hb

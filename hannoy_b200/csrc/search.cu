@@ -22,6 +22,10 @@
 #include "ring.cuh"
 #include "sorted.cuh"
 
+#ifndef HB_MIN_BLOCKS_F32
+#define HB_MIN_BLOCKS_F32 3  // resident CTAs per SM the f32 kernel is compiled for (register budget)
+#endif
+
 namespace hb {
 
 // Optional phase timers (build with -DHB_PHASES; dev only): cycles per phase summed over all queries.
@@ -35,6 +39,16 @@ __device__ unsigned long long g_phase[16];
 #define PH_ADD(c, i) {}
 #define PH_RESET
 #endif
+// Optional event trace of ONE warp (build with -DHB_TRACE; dev only): (clock64 << 8 | event) records.
+#ifdef HB_TRACE
+#define HB_TRACE_CAP (1 << 18)
+__device__ unsigned long long g_trace[HB_TRACE_CAP];
+__device__ unsigned int g_trace_n;
+#define TR(c, ev) { if ((c).tr && lane_id() == 0) { unsigned int tn_ = g_trace_n; if (tn_ < HB_TRACE_CAP) { g_trace[tn_] = ((unsigned long long)clock64() << 8) | (ev); g_trace_n = tn_ + 1; } } }
+#else
+#define TR(c, ev) {}
+#endif
+enum { TR_QSTART = 1, TR_POP = 2, TR_ADJ = 3, TR_VIS = 4, TR_POSTED = 5, TR_ROWWAIT = 6, TR_GROUP = 7, TR_HEAP = 8, TR_QEND = 9, TR_L0 = 10 };
 enum { PH_STAGE = 0, PH_UPPER = 1, PH_ADJ = 2, PH_VIS = 3, PH_ROWS = 4, PH_HEAP = 5, PH_TAIL = 6, PH_TOTAL = 7, PH_N = 8 };
 
 struct Ctx {
@@ -45,6 +59,7 @@ struct Ctx {
     const float* qs; float qn;            // query (device layout) in shared memory, query header norm
     uint32_t excl;                        // by_item: slot removed from the candidates, else UINT32_MAX
     bool overflow;
+    bool tr;                              // this warp writes the event trace (HB_TRACE builds)
     RowRing& ring;                        // per-warp, lives across queries (barrier phases persist)
 #ifdef HB_PHASES
     long long ph[PH_N];
@@ -56,15 +71,22 @@ struct Ctx {
 
 __device__ __forceinline__ float key_dist(u64 k) { return __uint_as_float((uint32_t)(k >> 32)); }
 
+// ---- one-by-one heap updates: the fallback for heaps of more than 32 * MERGE_TILES entries (large ef, pass 1) ----
+// Kept out of line (cold): it works on a copy of the heap state so that Ctx never has its address taken.
+struct Heaps {
+    u64* res; int res_len, res_cap;
+    u64* que; int q_len, q_cap;
+    int pass; bool overflow;
+};
 // res.push (unconditional)
-__device__ __forceinline__ void res_push(Ctx& c, u64 key) {
+__device__ __forceinline__ void res_push(Heaps& c, u64 key) {
     if (c.res_len >= c.res_cap) { c.overflow = true; return; }
     int pos = count_lt(c.res, c.res_len, key);
     insert_at(c.res, c.res_len, pos, key);
     c.res_len++;
 }
 // `if res.len() == ef { push_pop_max } else { push }` — reader.rs:360-364
-__device__ __forceinline__ void res_accept(Ctx& c, u64 key, int ef) {
+__device__ __forceinline__ void res_accept(Heaps& c, u64 key, int ef) {
     if (c.res_len == ef) {
         if (ef == 0) return;                      // push_pop_max on an empty heap returns the item
         if (key > c.res[c.res_len - 1]) return;   // pushed and popped straight away
@@ -83,15 +105,15 @@ __device__ __forceinline__ void res_accept(Ctx& c, u64 key, int ef) {
 // dropping the sentinel changes nothing; a negative distance (only BinaryQuantizedCosine can produce one,
 // binary_quantized_cosine.rs:49-58 has no clamp) sorts last by bits yet passes `f > f_max`, so the first
 // negative distance seen in the pruning pass sends the query to pass 1, which never prunes.
-__device__ __forceinline__ bool is_dead(const Ctx& c, uint32_t bits, int ef) {
-    if (c.p.pass != 0) return false;
+__device__ __forceinline__ bool is_dead(const Heaps& c, uint32_t bits, int ef) {
+    if (c.pass != 0) return false;
     if (c.res_len < ef || c.res_len == 0) return false;
     uint32_t mb = (uint32_t)(c.res[c.res_len - 1] >> 32);
     if ((bits | mb) & 0x80000000u) return false;
     return __uint_as_float(bits) > __uint_as_float(mb);
 }
 // search_queue.push — reader.rs:319,354
-__device__ __forceinline__ void queue_push(Ctx& c, uint32_t bits, uint32_t slot, int ef) {
+__device__ __forceinline__ void queue_push(Heaps& c, uint32_t bits, uint32_t slot, int ef) {
     if (is_dead(c, bits, ef)) return;
     u64 qk = ((u64)bits << 32) | (uint32_t)(~slot);
     if (c.q_len == c.q_cap) {
@@ -105,6 +127,24 @@ __device__ __forceinline__ void queue_push(Ctx& c, uint32_t bits, uint32_t slot,
         insert_at(c.que, c.q_len, pos, qk);
         c.q_len++;
     }
+}
+enum ChunkMode { CH_EP, CH_NBR, CH_LINEAR };
+__device__ __noinline__ void heaps_update_seq(Heaps* hp, int mode, int ef, unsigned resm, unsigned accm, uint32_t bits, uint32_t s) {
+    Heaps h = *hp;
+    const u64 key = ((u64)bits << 32) | s;
+    for (unsigned m = resm; m; m &= m - 1) {
+        u64 k = __shfl_sync(FULL, key, __ffs(m) - 1);
+        if (mode == CH_EP) res_push(h, k);       // reader.rs:322-324: unconditional
+        else res_accept(h, k, ef);
+    }
+    if (mode != CH_LINEAR) {
+        for (unsigned m = accm; m; m &= m - 1) {
+            int src = __ffs(m) - 1;
+            uint32_t b = __shfl_sync(FULL, bits, src), sl = __shfl_sync(FULL, s, src);
+            queue_push(h, b, sl, ef);
+        }
+    }
+    *hp = h;
 }
 
 // ---- visited set --------------------------------------------------------------------------------------
@@ -149,214 +189,250 @@ __device__ __forceinline__ bool passes_filter(const Ctx& c, uint32_t s, bool fil
 }
 
 // ---- distances of one chunk (<= 32 rows, one per lane) -----------------------------------------------------
+// Split in two so that a caller can do unrelated work (the previous expansion's heap update) while the first
+// rows are on their way: rows_begin posts / prefetches, rows_finish consumes and returns the lane's distance.
+struct RowsInFlight {
+    unsigned mask;        // lanes that own a live row
+    int n_live, rank;     // number of live rows, this lane's rank among them
+    bool has;
+    const uint8_t* grow;  // this lane's row in global memory
+    float in;             // this lane's item header (norm)
+};
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <int KIND>
-__device__ __forceinline__ float chunk_distances(Ctx& c, unsigned mask, uint32_t s) {
+__device__ __forceinline__ void rows_begin(Ctx& c, unsigned mask, uint32_t s, RowsInFlight& rf) {
+    const DevIndex& ix = c.p.ix;
+    const int lane = lane_id();
+    rf.mask = mask;
+    rf.n_live = __popc(mask);
+    rf.has = (mask >> lane) & 1;
+    rf.rank = __popc(mask & ((1u << lane) - 1));
+    rf.grow = ix.rows + (size_t)s * ix.row_stride;
+    rf.in = 0.0f;
+    if (!rf.has) return;
+    if (KIND == KIND_F32_WARP) {
+        // Row r (in ascending-lane order) lands in ring slot r % S: the first S copies are posted at once by the
+        // lanes that own them.
+        if (rf.rank < (int)c.ring.slots) c.ring.post(rf.rank, rf.grow, ix.row_stride);
+        if (ix.metric == HB_COSINE) rf.in = __ldg(&ix.hdr[s]);
+    } else {
+        for (uint32_t o = 0; o < ix.row_stride; o += 128) prefetch_l2(rf.grow + o);
+        if (ix.metric == HB_COSINE || ix.metric == HB_BQ_COSINE) rf.in = __ldg(&ix.hdr[s]);
+    }
+}
+
+template <int KIND>
+__device__ __forceinline__ float rows_finish(Ctx& c, const RowsInFlight& rf, uint32_t s) {
     const DevIndex& ix = c.p.ix;
     const int lane = lane_id();
     float mine = 0.0f;
     if (KIND == KIND_F32_WARP && c.ring.slots == 0) {
         // rows too long for the shared-memory ring: 4 rows at a time straight from global memory
-        unsigned m = mask;
+        unsigned m = rf.mask;
         while (m) {
             int l[4];
-            uint32_t sl[4];
             const uint8_t* rowp[4];
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 if (m) { l[r] = __ffs(m) - 1; m &= m - 1; } else l[r] = -1;
-                sl[r] = __shfl_sync(FULL, s, l[r] < 0 ? l[0] : l[r]);
-                rowp[r] = ix.rows + (size_t)sl[r] * ix.row_stride;
+                uint32_t sl = __shfl_sync(FULL, s, l[r] < 0 ? l[0] : l[r]);
+                rowp[r] = ix.rows + (size_t)sl * ix.row_stride;
             }
             float raw[4];
             if (ix.metric == HB_COSINE) warp_rows_raw<4, true, false>(ix, c.qs, rowp, raw);
             else warp_rows_raw<4, false, false>(ix, c.qs, rowp, raw);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if (lane == l[r]) {
-                    float in = (ix.metric == HB_COSINE) ? __ldg(&ix.hdr[sl[r]]) : 0.0f;
-                    mine = finish_f32(ix.metric, raw[r], c.qn, in);
-                }
-            }
+            for (int r = 0; r < 4; ++r)
+                if (lane == l[r]) mine = finish_f32(ix.metric, raw[r], c.qn, rf.in);
         }
     } else if (KIND == KIND_F32_WARP) {
-        // Row r (in ascending-lane order) lands in ring slot r % S.  The first S copies are posted at once by
-        // the lanes that own them; slot group g is re-posted as soon as its ROW_GROUP rows were consumed.
+        // slot group g is re-posted as soon as its ROW_GROUP rows were consumed
         const int S = (int)c.ring.slots;
-        const int n_live = __popc(mask);
-        const bool has = (mask >> lane) & 1;
-        const int rank = __popc(mask & ((1u << lane) - 1));
-        const uint8_t* grow = ix.rows + (size_t)s * ix.row_stride;
-        if (has && rank < S) c.ring.post(rank, grow, ix.row_stride);
-        const float in = (has && ix.metric == HB_COSINE) ? __ldg(&ix.hdr[s]) : 0.0f;
         int slot0 = 0;
-        for (int r0 = 0; r0 < n_live; r0 += ROW_GROUP) {
-            const int g = min(ROW_GROUP, n_live - r0);
+        float myraw = 0.0f;
+        for (int r0 = 0; r0 < rf.n_live; r0 += ROW_GROUP) {
+            const int g = min(ROW_GROUP, rf.n_live - r0);
             const uint8_t* rowp[ROW_GROUP];
 #pragma unroll
             for (int r = 0; r < ROW_GROUP; ++r) {
-                if (r < g) c.ring.wait(slot0 + r);
+                if (r < g) { c.ring.wait(slot0 + r); TR(c, TR_ROWWAIT) }
                 rowp[r] = c.ring.ptr + (size_t)(slot0 + (r < g ? r : 0)) * c.ring.stride;
             }
-            float raw[ROW_GROUP];
-            if (ix.metric == HB_COSINE) warp_rows_raw<ROW_GROUP, true, true>(ix, c.qs, rowp, raw);
-            else warp_rows_raw<ROW_GROUP, false, true>(ix, c.qs, rowp, raw);
+            // row r's sum comes back on lane group_owner(r); the lane that owns the row picks it up
+            float red = (ix.metric == HB_COSINE) ? warp_rows_group<ROW_GROUP, true>(ix, c.qs, rowp) : warp_rows_group<ROW_GROUP, false>(ix, c.qs, rowp);
             __syncwarp();  // every lane has read the group's slots: they may be overwritten
-            const int nxt = rank - r0 - S;
-            if (has && nxt >= 0 && nxt < g) c.ring.post(slot0 + nxt, grow, ix.row_stride);
-#pragma unroll
-            for (int r = 0; r < ROW_GROUP; ++r)
-                if (has && rank == r0 + r) mine = finish_f32(ix.metric, raw[r], c.qn, in);
+            const int nxt = rf.rank - r0 - S;
+            if (rf.has && nxt >= 0 && nxt < g) c.ring.post(slot0 + nxt, rf.grow, ix.row_stride);
+            const int mr = rf.rank - r0;
+            const float got = __shfl_sync(FULL, red, group_owner<ROW_GROUP>(mr >= 0 && mr < ROW_GROUP ? mr : 0));
+            if (rf.has && mr >= 0 && mr < g) myraw = got;
             slot0 += ROW_GROUP;
             if (slot0 >= S) slot0 = 0;
+            TR(c, TR_GROUP)
         }
+        if (rf.has) mine = finish_f32(ix.metric, myraw, c.qn, rf.in);
     } else if (KIND == KIND_F32_LANE) {
-        if (mask >> lane & 1) {
-            const float* row = reinterpret_cast<const float*>(ix.rows + (size_t)s * ix.row_stride);
-            float in = (ix.metric == HB_COSINE) ? __ldg(&ix.hdr[s]) : 0.0f;
-            mine = lane_distance_f32<true>(ix, c.qs, c.qn, row, in);
-        }
+        if (rf.has) mine = lane_distance_f32<true>(ix, c.qs, c.qn, reinterpret_cast<const float*>(rf.grow), rf.in);
     } else {
-        if (mask >> lane & 1) {
-            const uint64_t* row = reinterpret_cast<const uint64_t*>(ix.rows + (size_t)s * ix.row_stride);
-            uint32_t h = lane_xor_popc(reinterpret_cast<const uint64_t*>(c.qs), row, ix.n_words);
-            float in = (ix.metric == HB_BQ_COSINE) ? __ldg(&ix.hdr[s]) : 0.0f;
-            mine = finish_bin(ix.metric, h, ix.n_words * 64u, c.qn, in);
+        if (rf.has) {
+            uint32_t h = lane_xor_popc(reinterpret_cast<const uint64_t*>(c.qs), reinterpret_cast<const uint64_t*>(rf.grow), ix.n_words);
+            mine = finish_bin(ix.metric, h, ix.n_words * 64u, c.qn, rf.in);
         }
     }
     return mine;
 }
 
-enum ChunkMode { CH_EP, CH_NBR, CH_LINEAR };
 constexpr int MERGE_TILES = 8;  // heaps of up to 256 entries are updated by one merge pass per chunk
 
 // One chunk of <= 32 points (lane i holds the i-th, ascending).  Mirrors, for all 32 at once, the body of
-// `for &ep in eps` (reader.rs:315-325), `for point in links.iter()` (reader.rs:342-366) or the
-// brute-force loop (reader.rs:683-705).
-template <int KIND, int MODE>
-__device__ __forceinline__ void process_chunk(Ctx& c, uint32_t s, bool valid, float f_max, int ef, bool filt, int lvl01) {
+// `for &ep in eps` (reader.rs:315-325; mode CH_EP), `for point in links.iter()` (reader.rs:342-366; CH_NBR) or
+// the brute-force loop (reader.rs:683-705; CH_LINEAR).  `mode` is warp-uniform; there is a single call site so
+// that the kernel holds one copy of the gather / distance / merge code.
+template <int KIND>
+__device__ __forceinline__ void process_chunk(Ctx& c, int mode, uint32_t s, bool valid, float f_max, int ef, bool filt, int lvl01) {
     const int lane = lane_id();
     bool live;
     PH_DECL
-    if (MODE == CH_NBR) live = vis_test_and_set(c, s, valid);           // `if !path.insert(point) { continue }`
-    else if (MODE == CH_EP) { vis_test_and_set(c, s, valid); live = valid; }  // path.insert(ep), result ignored
+    if (mode == CH_NBR) live = vis_test_and_set(c, s, valid);           // `if !path.insert(point) { continue }`
+    else if (mode == CH_EP) { vis_test_and_set(c, s, valid); live = valid; }  // path.insert(ep), result ignored
     else live = valid;
     unsigned lm = __ballot_sync(FULL, live);
     if (lvl01) PH_ADD(c, PH_VIS)
+    TR(c, TR_VIS)
     if (!lm) return;
     c.cur_dist += __popc(lm);
-    float dist = chunk_distances<KIND>(c, lm, s);
+    RowsInFlight rf;
+    rows_begin<KIND>(c, lm, s, rf);
+    TR(c, TR_POSTED)
+    float dist = rows_finish<KIND>(c, rf, s);
     uint32_t bits = __float_as_uint(dist);
     if (lvl01) PH_ADD(c, PH_ROWS)
-    if (MODE != CH_LINEAR && c.p.pass == 0 && __ballot_sync(FULL, live && (bits >> 31))) { c.overflow = true; return; }
-    bool pf = live && passes_filter(c, s, filt);
-    bool acc;
-    if (MODE == CH_NBR) {
+    if (mode != CH_LINEAR && c.p.pass == 0 && __ballot_sync(FULL, live && (bits >> 31))) { c.overflow = true; return; }
+
+    // which points are accepted (`acc`: pushed to the search queue) and which of those may enter the result set
+    // (`pf`: candidate filter) — reader.rs:322,353,355-359
+    const bool pf = live && passes_filter(c, s, filt);
+    bool acc = live;
+    if (mode == CH_NBR) {
         // `res.len() < self.ef || dist < f_max` with live len and stale f_max (reader.rs:353): the first
         // ef - len filter-passing points in ascending order are taken unconditionally.
         unsigned pfm = __ballot_sync(FULL, pf);
         int before = __popc(pfm & ((1u << lane) - 1));
         bool fill = (c.res_len + before) < ef;
         acc = live && (fill || dist < f_max);
-    } else {
-        acc = live;
     }
-    unsigned accm = __ballot_sync(FULL, acc);
-    unsigned resm = __ballot_sync(FULL, acc && pf);
-    u64 key = ((u64)bits << 32) | s;
+    const unsigned accm = __ballot_sync(FULL, acc);
+    const unsigned resm = __ballot_sync(FULL, acc && pf);
     if (c.res_len <= 32 * MERGE_TILES && c.q_len <= 32 * MERGE_TILES) {
         // All accepted points of the chunk enter the heaps in one merge pass each (sorted.cuh merge_batch).
         // Result set: pushing the keys one by one with `if len == ef { push_pop_max } else { push }` leaves the
         // min(ef, len + m) smallest of the union when len <= ef, and the whole union when len > ef (or for entry points).
         const int m_res = __popc(resm);
-        int target = (MODE == CH_EP || c.res_len > ef) ? c.res_len + m_res : min(ef, c.res_len + m_res);
+        int target = (mode == CH_EP || c.res_len > ef) ? c.res_len + m_res : min(ef, c.res_len + m_res);
         if (target > c.res_cap) { c.overflow = true; return; }
-        if (m_res) c.res_len = merge_batch<false, false, MERGE_TILES>(c.res, c.res_len, acc && pf, key, target, 0u, nullptr);
-        if (MODE == CH_LINEAR) return;
-        // Queue: entries that can never be popped (is_dead, judged against the UPDATED result set) are not pushed,
-        // and old ones — they sit at the front of the descending array — are trimmed in the same pass.
-        const bool prune = c.p.pass == 0 && c.res_len >= ef && c.res_len > 0 && !(c.res[c.res_len - 1] >> 63);
-        const uint32_t mb = prune ? (uint32_t)(c.res[c.res_len - 1] >> 32) : 0xffffffffu;
-        const bool qhas = acc && !(prune && !(bits >> 31) && bits > mb);
-        const int mq = __popc(__ballot_sync(FULL, qhas));
-        if (c.q_len + mq > c.q_cap) {
-            int d0 = 0;
-            if (prune) {
-                for (int i = lane; i < c.q_len; i += 32) d0 += (uint32_t)(c.que[i] >> 32) > mb;
-                d0 = __reduce_add_sync(FULL, d0);
+        if (m_res) c.res_len = merge_batch<false, false, MERGE_TILES>(c.res, c.res_len, acc && pf, ((u64)bits << 32) | s, target, 0u);
+        if (mode != CH_LINEAR) {
+            // Queue: entries that can never be popped (is_dead, judged against the UPDATED result set) are not
+            // pushed, and old ones — they sit at the front of the descending array — are trimmed in the same pass.
+            const bool prune = c.p.pass == 0 && c.res_len >= ef && c.res_len > 0 && !(c.res[c.res_len - 1] >> 63);
+            const uint32_t mb = prune ? (uint32_t)(c.res[c.res_len - 1] >> 32) : 0xffffffffu;
+            const bool qhas = acc && !(prune && !(bits >> 31) && bits > mb);
+            const int mq = __popc(__ballot_sync(FULL, qhas));
+            if (c.q_len + mq > c.q_cap) {
+                int d0 = 0;
+                if (prune) {
+                    for (int i = lane; i < c.q_len; i += 32) d0 += (uint32_t)(c.que[i] >> 32) > mb;
+                    d0 = __reduce_add_sync(FULL, d0);
+                }
+                if (c.q_len + mq - d0 > c.q_cap) { c.overflow = true; return; }  // would have to drop a live entry
             }
-            if (c.q_len + mq - d0 > c.q_cap) { c.overflow = true; return; }  // would have to drop a live entry
+            if (mq || prune)
+                c.q_len = merge_batch<true, true, MERGE_TILES>(c.que, c.q_len, qhas, ((u64)bits << 32) | (uint32_t)(~s), c.q_cap, mb);
         }
-        if (mq || prune)
-            c.q_len = merge_batch<true, true, MERGE_TILES>(c.que, c.q_len, qhas, ((u64)bits << 32) | (uint32_t)(~s), c.q_cap, mb, nullptr);
     } else {
-        for (unsigned m = resm; m; m &= m - 1) {
-            u64 k = __shfl_sync(FULL, key, __ffs(m) - 1);
-            if (MODE == CH_EP) res_push(c, k);       // reader.rs:322-324: unconditional
-            else res_accept(c, k, ef);
-        }
-        if (MODE == CH_LINEAR) return;
-        for (unsigned m = accm; m; m &= m - 1) {
-            int src = __ffs(m) - 1;
-            uint32_t b = __shfl_sync(FULL, bits, src), sl = __shfl_sync(FULL, s, src);
-            queue_push(c, b, sl, ef);
-        }
+        Heaps h{c.res, c.res_len, c.res_cap, c.que, c.q_len, c.q_cap, c.p.pass, false};
+        heaps_update_seq(&h, mode, ef, resm, accm, bits, s);
+        c.res_len = h.res_len;
+        c.q_len = h.q_len;
+        if (h.overflow) c.overflow = true;
     }
     if (lvl01) PH_ADD(c, PH_HEAP)
+    TR(c, TR_HEAP)
 }
 
-// Visitor::visit — reader.rs:301-369.  Entry points: `eps` (n_eps slots in global memory) or `single`.
+// Visitor::visit — reader.rs:301-369 — and, with `linear`, the candidate loop of brute_force_search
+// (reader.rs:683-705).  Entry points: `eps` (n_eps slots in global memory) or `single`.
+// One loop feeds process_chunk: first the entry points (or the linear-scan candidates), then one chunk per
+// expansion — layer 0 reads the fixed-stride adjacency line (the line of the most likely next pop is requested
+// ahead), the other layers and irregular layer-0 graphs walk the CSR lists.
 template <int KIND>
-__device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_eps, uint32_t single, uint32_t level, int ef, bool filt) {
+__device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_eps, uint32_t single, uint32_t level, int ef, bool filt, bool linear) {
     const DevIndex& ix = c.p.ix;
     const int lane = lane_id();
     const int l01 = level ? 0 : 1;
     c.res_len = 0;
     c.q_len = 0;
     c.cur_dist = c.cur_exp = c.cur_deg = 0;
-    if (eps) {
-        for (uint32_t base = 0; base < n_eps; base += 32) {
-            bool valid = base + lane < n_eps;
-            uint32_t s = valid ? __ldg(&eps[base + lane]) : 0;
-            process_chunk<KIND, CH_EP>(c, s, valid, FLT_MAX, ef, filt, l01);
-        }
-    } else {
-        process_chunk<KIND, CH_EP>(c, single, lane == 0, FLT_MAX, ef, filt, l01);
-    }
+    const uint32_t* list = linear ? c.p.cand_slots : eps;
+    const uint32_t n_first = linear ? c.p.n_cand_slots : (eps ? n_eps : 1u);
+    uint32_t base0 = 0;
     const uint32_t* off = ix.off[level];
     const uint32_t* nbr = ix.nbr[level];
     const uint32_t* nbrx = level == 0 ? ix.nbr0x : nullptr;
     uint32_t spec_cs = 0xffffffffu, spec_adj = 0xffffffffu;  // adjacency line requested ahead of its pop
-    while (c.q_len > 0 && !c.overflow) {
-        u64 top = c.que[c.q_len - 1];
-        float f = key_dist(top);
-        float f_max = c.res_len ? key_dist(c.res[c.res_len - 1]) : FLT_MAX;
-        if (f > f_max) break;
-        c.q_len--;
-        uint32_t cs = ~(uint32_t)top;
-        c.cur_exp += 1;
-        if (nbrx) {
-            PH_DECL
-            uint32_t s = (cs == spec_cs) ? spec_adj : __ldg(&nbrx[(size_t)cs * FIXED_DEG + lane]);
-            bool valid = s != 0xffffffffu;
-            c.cur_deg += __popc(__ballot_sync(FULL, valid));
-            PH_ADD(c, PH_ADJ)
-            // the entry now on top of the queue is popped next unless one of cs's neighbours beats it
-            if (c.q_len > 0) {
-                spec_cs = ~(uint32_t)c.que[c.q_len - 1];
-                spec_adj = __ldg(&nbrx[(size_t)spec_cs * FIXED_DEG + lane]);
-            } else {
-                spec_cs = 0xffffffffu;
-            }
-            process_chunk<KIND, CH_NBR>(c, valid ? s : 0, valid, f_max, ef, filt, l01);
+    uint32_t csr_pos = 0, csr_end = 0;                       // rest of the CSR list being expanded
+    float f_max = FLT_MAX;
+    while (!c.overflow) {
+        int mode;
+        uint32_t s;
+        bool valid;
+        PH_DECL
+        if (base0 < n_first) {
+            valid = base0 + lane < n_first;
+            s = !valid ? 0 : (list ? __ldg(&list[base0 + lane]) : single);
+            base0 += 32;
+            mode = linear ? CH_LINEAR : CH_EP;
         } else {
-            uint32_t b = __ldg(&off[cs]), e = __ldg(&off[cs + 1]);
-            c.cur_deg += e - b;
-            for (uint32_t base = b; base < e; base += 32) {
-                bool valid = base + lane < e;
-                uint32_t s = valid ? __ldg(&nbr[base + lane]) : 0;
-                process_chunk<KIND, CH_NBR>(c, s, valid, f_max, ef, filt, l01);
+            if (linear) break;
+            mode = CH_NBR;
+            if (csr_pos >= csr_end) {
+                if (c.q_len == 0) break;
+                u64 top = c.que[c.q_len - 1];
+                float f = key_dist(top);
+                f_max = c.res_len ? key_dist(c.res[c.res_len - 1]) : FLT_MAX;
+                if (f > f_max) break;
+                c.q_len--;
+                uint32_t cs = ~(uint32_t)top;
+                c.cur_exp += 1;
+                TR(c, TR_POP)
+                if (nbrx) {
+                    s = (cs == spec_cs) ? spec_adj : __ldg(&nbrx[(size_t)cs * FIXED_DEG + lane]);
+                    // the entry now on top of the queue is popped next unless one of cs's neighbours beats it
+                    if (c.q_len > 0) {
+                        spec_cs = ~(uint32_t)c.que[c.q_len - 1];
+                        spec_adj = __ldg(&nbrx[(size_t)spec_cs * FIXED_DEG + lane]);
+                    } else {
+                        spec_cs = 0xffffffffu;
+                    }
+                } else {
+                    csr_pos = __ldg(&off[cs]);
+                    csr_end = __ldg(&off[cs + 1]);
+                    if (csr_pos >= csr_end) continue;
+                }
             }
+            if (!nbrx) {
+                s = csr_pos + lane < csr_end ? __ldg(&nbr[csr_pos + lane]) : 0xffffffffu;
+                csr_pos += 32;
+            }
+            valid = s != 0xffffffffu;
+            if (!valid) s = 0;
+            c.cur_deg += __popc(__ballot_sync(FULL, valid));
+            if (l01) PH_ADD(c, PH_ADJ)
+            TR(c, TR_ADJ)
         }
+        process_chunk<KIND>(c, mode, s, valid, f_max, ef, filt, l01);
     }
     if (level) { c.n_dist_up += c.cur_dist; c.n_exp_up += c.cur_exp; c.n_deg_up += c.cur_deg; }
     else { c.n_dist_l0 += c.cur_dist; c.n_exp_l0 += c.cur_exp; c.n_deg_l0 += c.cur_deg; }
@@ -473,6 +549,11 @@ __device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64*
     c.touched = p.touched + (size_t)slot_idx * p.touched_cap;
     c.touched_len = 0; c.touched_over = false;
     c.excl = 0xffffffffu; c.overflow = false;
+    c.tr = false;
+#ifdef HB_TRACE
+    c.tr = slot_idx == 777 && p.pass == 0;
+#endif
+    TR(c, TR_QSTART)
     c.n_dist_up = c.n_exp_up = c.n_deg_up = c.n_dist_l0 = c.n_exp_l0 = c.n_deg_l0 = 0;
     c.cur_dist = c.cur_exp = c.cur_deg = 0;
     u64 flags = p.pass ? HB_FLAG_SLOW_PATH : 0;
@@ -492,26 +573,20 @@ __device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64*
     PH_ADD(c, PH_STAGE)
 
     int n_out = 0;
-    if (p.mode >= 2) {
-        // brute_force_search over the candidate slots (ascending) — reader.rs:668-711
-        flags |= HB_FLAG_LINEAR;
-        for (uint32_t base = 0; base < p.n_cand_slots; base += 32) {
-            bool valid = base + lane < p.n_cand_slots;
-            uint32_t s = valid ? __ldg(&p.cand_slots[base + lane]) : 0;
-            process_chunk<KIND, CH_LINEAR>(c, s, valid, FLT_MAX, (int)count, false, 1);
-        }
-        c.n_dist_l0 += c.cur_dist;
-        n_out = c.res_len;
-    } else {
+    {
         // One call site of visit() drives the whole search as a small state machine:
         //   ST_UPPER  greedy descent, ef = 1, levels max_level..1, shared visited set (reader.rs:732-741)
         //   ST_L0     the ef-bounded layer-0 walk (reader.rs:743-767) / by_item's seeded walk (reader.rs:842-862)
         //   ST_FB     exhaustive fallback, one visit per unseen item (reader.rs:771-795 / 865-889)
-        enum { ST_UPPER, ST_L0, ST_FB };
+        //   ST_LIN    brute_force_search over the candidate slots, ascending (reader.rs:668-711)
+        enum { ST_UPPER, ST_L0, ST_FB, ST_LIN };
         uint32_t ep_single = 0, level = 0;
         const uint32_t* eps = ix.eps;
         int st = ST_L0;
-        if (p.mode & 1) {  // nns_by_item — reader.rs:836-842
+        if (p.mode >= 2) {
+            st = ST_LIN;
+            flags |= HB_FLAG_LINEAR;
+        } else if (p.mode & 1) {  // nns_by_item — reader.rs:836-842
             c.excl = p.q_slots[qi];
             ep_single = c.excl;
             eps = nullptr;
@@ -527,9 +602,10 @@ __device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64*
         for (;;) {
             bool filt = true;
             if (st == ST_UPPER) { ef = 1; filt = false; }
-            else if (st == ST_L0) { ef = ef0; level = 0; }
-            visit<KIND>(c, eps, ix.n_ep, ep_single, level, ef, filt);
-            if (c.overflow) break;
+            else if (st == ST_L0) { ef = ef0; level = 0; TR(c, TR_L0) }
+            else if (st == ST_LIN) { ef = (int)count; level = 0; filt = false; }
+            visit<KIND>(c, eps, ix.n_ep, ep_single, level, ef, filt, st == ST_LIN);
+            if (c.overflow || st == ST_LIN) break;
             if (st == ST_UPPER) {
                 bool found = c.res_len != 0;       // reference: expect("No neighbor was found")
                 if (found) { ep_single = (uint32_t)c.res[0]; eps = nullptr; }  // peek_min
@@ -598,6 +674,7 @@ __device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64*
         }
     }
     __syncwarp();
+    TR(c, TR_QEND)
 #ifdef HB_PHASES
     PH_ADD(c, PH_TAIL)
     c.ph[PH_TOTAL] = clock64() - ph_q0;
@@ -608,7 +685,7 @@ __device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64*
 
 // Shared memory of one warp: [row ring][ring barriers][query][heaps (pass 0 only)].
 template <int KIND>
-__global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, KIND == KIND_F32_WARP ? 3 : 4) hnsw_search_kernel(const __grid_constant__ SearchParams p) {
+__global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, KIND == KIND_F32_WARP ? HB_MIN_BLOCKS_F32 : 4) hnsw_search_kernel(const __grid_constant__ SearchParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp_in_block = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
@@ -654,6 +731,22 @@ void read_phases(unsigned long long* out) {
     cudaMemcpyFromSymbol(out, g_phase, sizeof(unsigned long long) * PH_N);
     unsigned long long z[16] = {};
     cudaMemcpyToSymbol(g_phase, z, sizeof(z));
+}
+
+// dev: copy out and reset the event trace (empty unless built with -DHB_TRACE)
+uint32_t read_trace(unsigned long long* out, uint32_t cap) {
+#ifdef HB_TRACE
+    unsigned int n = 0;
+    cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(n));
+    if (n > cap) n = cap;
+    if (n) cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * n);
+    unsigned int z = 0;
+    cudaMemcpyToSymbol(g_trace_n, &z, sizeof(z));
+    return n;
+#else
+    (void)out; (void)cap;
+    return 0;
+#endif
 }
 
 __global__ void fill_iota_kernel(uint32_t* list, uint32_t* n_out, uint32_t n) {

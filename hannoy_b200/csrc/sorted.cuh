@@ -73,9 +73,10 @@ __device__ __forceinline__ void topk_insert(u64* a, int& len, int cap, u64 key) 
 //   drop_above (TRIM only) old entries whose distance bits exceed it are dropped: they sit at the front of a
 //              descending array
 //   keep       final length is capped to `keep` (the entries that sort last are dropped)
-// Needs len <= 32 * MAX_TILES.  Returns the new length; *n_trimmed = entries dropped at the front.
+// Needs len <= 32 * MAX_TILES.  Returns the new length.  Out of line on purpose: one copy per heap kind keeps the
+// search kernel's hot loop small (instruction cache), and the arguments are plain values.
 template <bool DESC, bool TRIM, int MAX_TILES>
-__device__ __forceinline__ int merge_batch(u64* a, int len, bool has, u64 key, int keep, uint32_t drop_above, int* n_trimmed) {
+__device__ __noinline__ int merge_batch(u64* a, int len, bool has, u64 key, int keep, uint32_t drop_above) {
     const int lane = lane_id();
     const unsigned hm = __ballot_sync(FULL, has);
     int pos = 0;
@@ -95,9 +96,12 @@ __device__ __forceinline__ int merge_batch(u64* a, int len, bool has, u64 key, i
 #pragma unroll
     for (int t = 0; t < MAX_TILES; ++t) {
         int i = t * 32 + lane;
-        v[t] = (i < len) ? a[i] : 0ull;
+        v[t] = 0ull;
         sh[t] = 0;
-        if (TRIM) d += __popc(__ballot_sync(FULL, i < len && (uint32_t)(v[t] >> 32) > drop_above));
+        if (t * 32 < len) {  // warp-uniform
+            if (i < len) v[t] = a[i];
+            if (TRIM) d += __popc(__ballot_sync(FULL, i < len && (uint32_t)(v[t] >> 32) > drop_above));
+        }
     }
     int rank = 0;
     for (unsigned m = hm; m; m &= m - 1) {
@@ -106,7 +110,8 @@ __device__ __forceinline__ int merge_batch(u64* a, int len, bool has, u64 key, i
         int pb = __shfl_sync(FULL, pos, src);
         rank += DESC ? (kb > key) : (kb < key);
 #pragma unroll
-        for (int t = 0; t < MAX_TILES; ++t) sh[t] += (pb <= t * 32 + lane);
+        for (int t = 0; t < MAX_TILES; ++t)
+            if (t * 32 < len) sh[t] += (pb <= t * 32 + lane);
     }
     __syncwarp();
     const int new_len = min(len + __popc(hm) - d, keep);
@@ -114,14 +119,13 @@ __device__ __forceinline__ int merge_batch(u64* a, int len, bool has, u64 key, i
     for (int t = 0; t < MAX_TILES; ++t) {
         int i = t * 32 + lane;
         int j = i + sh[t] - d;
-        if (i < len && j >= 0 && j < new_len) a[j] = v[t];
+        if (t * 32 < len && i < len && j >= 0 && j < new_len) a[j] = v[t];
     }
     if (has) {
         int j = pos + rank - d;
         if (j >= 0 && j < new_len) a[j] = key;
     }
     __syncwarp();
-    if (n_trimmed) *n_trimmed = d;
     return new_len;
 }
 

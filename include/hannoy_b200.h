@@ -153,6 +153,9 @@ hb_status hb_tune(const char* key, int value);
  * (stage, upper layers, adjacency wait, visited filter, row gather+distance, heap update, tail, total).
  * All zero unless the library was built with -DHB_PHASES. */
 void hb_debug_phases(uint64_t* out8);
+/* Development aid: event trace (clock64 << 8 | event id) of one query warp since the last call; returns the
+ * number of records copied.  Always 0 unless the library was built with -DHB_TRACE. */
+uint32_t hb_debug_trace(uint64_t* out, uint32_t cap);
 
 const char* hb_last_error(void);
 

@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--sweep", default="")
     ap.add_argument("--parity", type=int, default=256)
     ap.add_argument("--out", default="")
+    ap.add_argument("--trace", default="", help="HB_TRACE builds: save the event trace of one warp over one step (.npy)")
+    ap.add_argument("--nq", type=int, default=0, help="override the batch size")
     args = ap.parse_args()
     import torch
     import hannoy_b200 as hb
@@ -35,6 +37,8 @@ def main():
     w = dict(bench.WORKLOADS[args.workload])
     if args.n_items:
         w["n"] = args.n_items
+    if args.nq:
+        w["nq"] = args.nq
     dev = torch.device("cuda", 0)
     threads = len(os.sched_getaffinity(0))
     log = lambda m: print(f"[sweep] {m}", file=sys.stderr, flush=True)
@@ -102,6 +106,14 @@ def main():
             names = ["stage", "upper", "adj", "vis", "rows", "heap", "tail", "total"]
             r["phase_frac"] = {n: round(float(p) / tot, 3) for n, p in zip(names, ph)}
             r["cycles_per_query"] = round(tot / (nq * args.steps))
+        if args.trace:
+            buf = np.zeros(1 << 18, np.uint64)
+            L.hb_debug_trace(buf.ctypes.data, len(buf))   # reset
+            step()
+            torch.cuda.synchronize()
+            n = L.hb_debug_trace(buf.ctypes.data, len(buf))
+            np.save(args.trace, buf[:n])
+            r["trace_events"] = int(n)
         results.append(r)
         print(json.dumps(r), flush=True)
     if args.out:
