@@ -71,8 +71,40 @@ class ShardedSearcher:
         torch.cuda.synchronize()
         return (o_ids.cpu().numpy().view(np.uint32), o_dist.cpu().numpy(), o_len.cpu().numpy().view(np.uint32))
 
+    def search_device(self, d_q, count, ef):
+        """Device-resident path (NCCL): `d_q` is a CUDA float32 tensor [nq, dims] holding ALL queries on this rank.
+        Local search on this rank's shard -> one all-gather of the padded per-shard top-k over NVLink -> k-way merge
+        kernel; everything stays in HBM and is ordered on the current stream.  Returns CUDA tensors
+        (ids int32 [nq, count] (bit pattern of the u32 ids), dist float32 [nq, count], len int32 [nq])."""
+        import torch
+        nq = d_q.shape[0]
+        dev = d_q.device
+        stream = torch.cuda.current_stream(dev)
+        ids = torch.full((nq, count), -1, dtype=torch.int32, device=dev)          # 0xFFFFFFFF = the merge sentinel
+        dist = torch.full((nq, count), float("inf"), dtype=torch.float32, device=dev)
+        lens = torch.empty((nq,), dtype=torch.int32, device=dev)
+        self.reader.search_device(d_q.data_ptr(), nq, count, max(ef, count), ids.data_ptr(), dist.data_ptr(), lens.data_ptr(),
+                                  None, stream.cuda_stream)
+        g_ids = torch.empty((self.world * nq, count), dtype=torch.int32, device=dev)   # == [world][nq][count]
+        g_dist = torch.empty((self.world * nq, count), dtype=torch.float32, device=dev)
+        self.dist.all_gather_into_tensor(g_ids, ids, group=self.group)
+        self.dist.all_gather_into_tensor(g_dist, dist, group=self.group)
+        from .reader import merge_topk_device
+        o_ids = torch.empty((nq, count), dtype=torch.int32, device=dev)
+        o_dist = torch.empty((nq, count), dtype=torch.float32, device=dev)
+        o_len = torch.empty((nq,), dtype=torch.int32, device=dev)
+        merge_topk_device(dev.index, g_ids.data_ptr(), g_dist.data_ptr(), self.world, nq, count, o_ids.data_ptr(),
+                          o_dist.data_ptr(), o_len.data_ptr(), stream.cuda_stream)
+        return o_ids, o_dist, o_len
+
     def search(self, q, count, ef):
         import torch
+        if self.reader is not None and self.dist.get_backend(self.group) == "nccl" and self.local_search == self._cuda_local_search:
+            dev = torch.device("cuda", self.device if self.device is not None else torch.cuda.current_device())
+            d_q = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32)).to(dev)
+            o_ids, o_dist, o_len = self.search_device(d_q, count, ef)
+            torch.cuda.synchronize(dev)
+            return (o_ids.cpu().numpy().view(np.uint32), o_dist.cpu().numpy(), o_len.cpu().numpy().view(np.uint32))
         ids, dist, lens = self.local_search(q, count, ef)[:3]
         ids, dist = pad_topk(ids, dist, lens, count)
         backend = self.dist.get_backend(self.group)

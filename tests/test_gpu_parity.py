@@ -80,3 +80,47 @@ def test_config1_shape():
     got = rd.nns(10).ef_search(64).by_vectors_raw(q, counters=True)
     assert_same(got, want, "config 1")
     assert_counters_same(got[3], want[3], "config 1")
+
+
+def test_id_sharded_search_merge_on_one_device():
+    """The id-sharded path with both shards on one GPU: per-shard device-resident search into padded
+    buffers, k-way merge kernel, against `reference reader on each shard index, merged by (distance bits, id)`."""
+    import torch
+    import hannoy_b200 as hb
+    from hannoy_b200.sharded import shard_of
+    rng = np.random.default_rng(0)
+    n, dims, k, ef, world = 3000, 48, 10, 40, 3
+    x = rng.normal(0, 1, (n, dims)).astype(np.float32)
+    ids = np.arange(n, dtype=np.uint32) * 5 + 2
+    q = rng.normal(0, 1, (130, dims)).astype(np.float32)
+    dev = torch.device("cuda", 0)
+    d_q = torch.from_numpy(q).to(dev)
+    nq = len(q)
+    g_ids = torch.full((world, nq, k), -1, dtype=torch.int32, device=dev)
+    g_dist = torch.full((world, nq, k), float("inf"), dtype=torch.float32, device=dev)
+    lens = torch.empty((nq,), dtype=torch.int32, device=dev)
+    parts, readers = [], []
+    from oracle.oracle import OracleDb
+    stream = torch.cuda.current_stream().cuda_stream
+    for s in range(world):
+        m = shard_of(ids, world) == s
+        db = OracleDb("euclidean", dims)
+        db.add_items(ids[m], x[m])
+        db.build(M=8, M0=16, ef_construction=40, seed=s)
+        rd = hb.Reader.from_arrays("euclidean", dims, db.ids(), db.rows(), db.headers(), db.layers(), db.entry_points, db.max_level, index=s)
+        readers.append(rd)
+        rd.search_device(d_q.data_ptr(), nq, k, ef, g_ids[s].data_ptr(), g_dist[s].data_ptr(), lens.data_ptr(), None, stream)
+        parts.append(db.search_by_vector(q, k, ef=ef))
+        torch.cuda.synchronize()
+        assert np.array_equal(g_ids[s].cpu().numpy().view(np.uint32), parts[-1][0]), f"shard {s}: device-resident search differs"
+    o_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    o_dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    o_len = torch.empty((nq,), dtype=torch.int32, device=dev)
+    hb.merge_topk_device(0, g_ids.data_ptr(), g_dist.data_ptr(), world, nq, k, o_ids.data_ptr(), o_dist.data_ptr(), o_len.data_ptr(), stream)
+    torch.cuda.synchronize()
+    gi, gd, gl = o_ids.cpu().numpy().view(np.uint32), o_dist.cpu().numpy().view(np.uint32), o_len.cpu().numpy()
+    for i in range(nq):
+        keys = sorted((int(p[1][i, j:j + 1].view(np.uint32)[0]), int(p[0][i, j])) for p in parts for j in range(int(p[2][i])))[:k]
+        assert gl[i] == len(keys)
+        assert gi[i, :len(keys)].tolist() == [kk[1] for kk in keys], f"query {i}"
+        assert gd[i, :len(keys)].tolist() == [kk[0] for kk in keys], f"query {i}"
