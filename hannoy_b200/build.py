@@ -21,7 +21,7 @@ FLAGS = [
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function",
 ]
 VARIANTS = {"": [], "phases": ["-DHB_PHASES"], "rg2": ["-DHB_ROW_GROUP=2"], "rg2phases": ["-DHB_ROW_GROUP=2", "-DHB_PHASES"],
-            "trace": ["-DHB_TRACE"], "rg2trace": ["-DHB_ROW_GROUP=2", "-DHB_TRACE"], "rg1": ["-DHB_ROW_GROUP=1"], "rg1b4": ["-DHB_ROW_GROUP=1", "-DHB_MIN_BLOCKS_F32=4"], "rg2b4": ["-DHB_ROW_GROUP=2", "-DHB_MIN_BLOCKS_F32=4"]}
+            "trace": ["-DHB_TRACE"], "mni": ["-DHB_MERGE_NOINLINE"], "nopf": ["-DHB_NO_ADJ_PREFETCH"], "rg2trace": ["-DHB_ROW_GROUP=2", "-DHB_TRACE"], "rg1": ["-DHB_ROW_GROUP=1"], "rg1b4": ["-DHB_ROW_GROUP=1", "-DHB_MIN_BLOCKS_F32=4"], "rg2b4": ["-DHB_ROW_GROUP=2", "-DHB_MIN_BLOCKS_F32=4"]}
 
 
 def out_path(variant=""):

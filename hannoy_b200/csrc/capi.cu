@@ -390,6 +390,7 @@ static hb_status run_search(const hb_index* ix, Workspace* w, SearchParams base,
     base.overflow_list = w->overflow_list; base.n_overflow = w->n_overflow;
     base.n_work = (uint32_t)nq;
     base.q_smem_bytes = (d.row_stride + 15) & ~15u;
+    base.defer = tunable("defer", 1);
     const uint32_t ef0 = std::max(base.ef_raw, base.count);
     if (d.kind == KIND_F32_WARP) {
         // rows in flight per warp: as many as fit the ring budget, in whole reduction groups

@@ -84,6 +84,7 @@ struct SearchParams {
     uint32_t q_smem_bytes = 0;         // per-warp query staging bytes
     uint32_t ring_slots = 0;           // KIND_F32_WARP: rows in flight per warp (multiple of ROW_GROUP), ring.cuh
     uint32_t ring_stride = 0;          // bytes between ring slots
+    int defer = 1;                     // layer 0, pass 0: overlap a chunk's heap update with the next pop's adjacency / visited traffic
 };
 #ifndef HB_ROW_GROUP
 #define HB_ROW_GROUP 4

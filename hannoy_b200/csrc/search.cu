@@ -148,13 +148,13 @@ __device__ __noinline__ void heaps_update_seq(Heaps* hp, int mode, int ef, unsig
 }
 
 // ---- visited set --------------------------------------------------------------------------------------
-__device__ __forceinline__ bool vis_test_and_set(Ctx& c, uint32_t s, bool valid) {
-    bool fresh = false;
-    if (valid) {
-        uint32_t bit = 1u << (s & 31);
-        uint32_t old = atomicOr(&c.vis[s >> 5], bit);
-        fresh = !(old & bit);
-    }
+// `path.insert(point)` in two halves so that independent work can sit between the atomic and its use:
+// vis_issue sends the atomicOr (returns the old word), vis_finish turns it into `fresh` and logs the touched slots.
+__device__ __forceinline__ uint32_t vis_issue(Ctx& c, uint32_t s, bool valid) {
+    return valid ? atomicOr(&c.vis[s >> 5], 1u << (s & 31)) : 0xffffffffu;
+}
+__device__ __forceinline__ bool vis_finish(Ctx& c, uint32_t s, bool valid, uint32_t old) {
+    const bool fresh = valid && !((old >> (s & 31)) & 1u);
     unsigned m = __ballot_sync(FULL, fresh);
     if (m) {
         uint32_t r = __popc(m & ((1u << lane_id()) - 1));
@@ -286,92 +286,89 @@ __device__ __forceinline__ float rows_finish(Ctx& c, const RowsInFlight& rf, uin
 
 constexpr int MERGE_TILES = 8;  // heaps of up to 256 entries are updated by one merge pass per chunk
 
-// One chunk of <= 32 points (lane i holds the i-th, ascending).  Mirrors, for all 32 at once, the body of
-// `for &ep in eps` (reader.rs:315-325; mode CH_EP), `for point in links.iter()` (reader.rs:342-366; CH_NBR) or
-// the brute-force loop (reader.rs:683-705; CH_LINEAR).  `mode` is warp-uniform; there is a single call site so
-// that the kernel holds one copy of the gather / distance / merge code.
-template <int KIND>
-__device__ __forceinline__ void process_chunk(Ctx& c, int mode, uint32_t s, bool valid, float f_max, int ef, bool filt, int lvl01) {
-    const int lane = lane_id();
-    bool live;
-    PH_DECL
-    if (mode == CH_NBR) live = vis_test_and_set(c, s, valid);           // `if !path.insert(point) { continue }`
-    else if (mode == CH_EP) { vis_test_and_set(c, s, valid); live = valid; }  // path.insert(ep), result ignored
-    else live = valid;
-    unsigned lm = __ballot_sync(FULL, live);
-    if (lvl01) PH_ADD(c, PH_VIS)
-    TR(c, TR_VIS)
-    if (!lm) return;
-    c.cur_dist += __popc(lm);
-    RowsInFlight rf;
-    rows_begin<KIND>(c, lm, s, rf);
-    TR(c, TR_POSTED)
-    float dist = rows_finish<KIND>(c, rf, s);
-    uint32_t bits = __float_as_uint(dist);
-    if (lvl01) PH_ADD(c, PH_ROWS)
-    if (mode != CH_LINEAR && c.p.pass == 0 && __ballot_sync(FULL, live && (bits >> 31))) { c.overflow = true; return; }
+__device__ __forceinline__ u64 warp_min_u64(u64 v) {
+    uint32_t hi = (uint32_t)(v >> 32);
+    uint32_t mhi = __reduce_min_sync(FULL, hi);
+    uint32_t lo = hi == mhi ? (uint32_t)v : 0xffffffffu;
+    uint32_t mlo = __reduce_min_sync(FULL, lo);
+    return ((u64)mhi << 32) | mlo;
+}
 
-    // which points are accepted (`acc`: pushed to the search queue) and which of those may enter the result set
-    // (`pf`: candidate filter) — reader.rs:322,353,355-359
-    const bool pf = live && passes_filter(c, s, filt);
-    bool acc = live;
-    if (mode == CH_NBR) {
-        // `res.len() < self.ef || dist < f_max` with live len and stale f_max (reader.rs:353): the first
-        // ef - len filter-passing points in ascending order are taken unconditionally.
-        unsigned pfm = __ballot_sync(FULL, pf);
-        int before = __popc(pfm & ((1u << lane) - 1));
-        bool fill = (c.res_len + before) < ef;
-        acc = live && (fill || dist < f_max);
-    }
-    const unsigned accm = __ballot_sync(FULL, acc);
-    const unsigned resm = __ballot_sync(FULL, acc && pf);
+// The heap update of one chunk of <= 32 points (lane i holds the i-th, ascending): what the bodies of
+// `for &ep in eps` (reader.rs:319-324; CH_EP), `for point in links.iter()` (reader.rs:354-364; CH_NBR) and the
+// brute-force loop (reader.rs:697-704; CH_LINEAR) do to `res` and `search_queue`, for all accepted points at once.
+// It is applied in two stages (result set, then queue) so that the caller can put memory operations of the NEXT
+// chunk between them.
+struct ChunkUpdate {
+    int mode;
+    bool acc;       // this lane's point is accepted: pushed to the search queue
+    bool pf;        // ... and passes the candidate filter: may enter the result set
+    bool qskip;     // this lane's point was popped straight away by the caller: not pushed (it still enters `res`)
+    bool seq_done;  // large heaps: stage A already applied both updates one by one
+    uint32_t bits, s;
+};
+
+__device__ __forceinline__ void heaps_stage_res(Ctx& c, ChunkUpdate& u, int ef) {
+    const unsigned resm = __ballot_sync(FULL, u.acc && u.pf);
+    u.seq_done = false;
     if (c.res_len <= 32 * MERGE_TILES && c.q_len <= 32 * MERGE_TILES) {
-        // All accepted points of the chunk enter the heaps in one merge pass each (sorted.cuh merge_batch).
-        // Result set: pushing the keys one by one with `if len == ef { push_pop_max } else { push }` leaves the
-        // min(ef, len + m) smallest of the union when len <= ef, and the whole union when len > ef (or for entry points).
+        // Pushing the keys one by one with `if len == ef { push_pop_max } else { push }` leaves the min(ef, len + m)
+        // smallest of the union when len <= ef, and the whole union when len > ef (or for entry points).
         const int m_res = __popc(resm);
-        int target = (mode == CH_EP || c.res_len > ef) ? c.res_len + m_res : min(ef, c.res_len + m_res);
+        int target = (u.mode == CH_EP || c.res_len > ef) ? c.res_len + m_res : min(ef, c.res_len + m_res);
         if (target > c.res_cap) { c.overflow = true; return; }
-        if (m_res) c.res_len = merge_batch<false, false, MERGE_TILES>(c.res, c.res_len, acc && pf, ((u64)bits << 32) | s, target, 0u);
-        if (mode != CH_LINEAR) {
-            // Queue: entries that can never be popped (is_dead, judged against the UPDATED result set) are not
-            // pushed, and old ones — they sit at the front of the descending array — are trimmed in the same pass.
-            const bool prune = c.p.pass == 0 && c.res_len >= ef && c.res_len > 0 && !(c.res[c.res_len - 1] >> 63);
-            const uint32_t mb = prune ? (uint32_t)(c.res[c.res_len - 1] >> 32) : 0xffffffffu;
-            const bool qhas = acc && !(prune && !(bits >> 31) && bits > mb);
-            const int mq = __popc(__ballot_sync(FULL, qhas));
-            if (c.q_len + mq > c.q_cap) {
-                int d0 = 0;
-                if (prune) {
-                    for (int i = lane; i < c.q_len; i += 32) d0 += (uint32_t)(c.que[i] >> 32) > mb;
-                    d0 = __reduce_add_sync(FULL, d0);
-                }
-                if (c.q_len + mq - d0 > c.q_cap) { c.overflow = true; return; }  // would have to drop a live entry
-            }
-            if (mq || prune)
-                c.q_len = merge_batch<true, true, MERGE_TILES>(c.que, c.q_len, qhas, ((u64)bits << 32) | (uint32_t)(~s), c.q_cap, mb);
-        }
+        if (m_res) c.res_len = merge_batch<false, false, MERGE_TILES>(c.res, c.res_len, u.acc && u.pf, ((u64)u.bits << 32) | u.s, target, 0u);
     } else {
+        const unsigned accm = __ballot_sync(FULL, u.acc && !u.qskip);
         Heaps h{c.res, c.res_len, c.res_cap, c.que, c.q_len, c.q_cap, c.p.pass, false};
-        heaps_update_seq(&h, mode, ef, resm, accm, bits, s);
+        heaps_update_seq(&h, u.mode, ef, resm, accm, u.bits, u.s);
         c.res_len = h.res_len;
         c.q_len = h.q_len;
         if (h.overflow) c.overflow = true;
+        u.seq_done = true;
     }
-    if (lvl01) PH_ADD(c, PH_HEAP)
-    TR(c, TR_HEAP)
+}
+__device__ __forceinline__ void heaps_stage_queue(Ctx& c, const ChunkUpdate& u, int ef) {
+    if (u.seq_done || u.mode == CH_LINEAR || c.overflow) return;
+    const int lane = lane_id();
+    // Entries that can never be popped (is_dead, judged against the UPDATED result set) are not pushed, and old
+    // ones — they sit at the front of the descending array — are trimmed in the same pass.
+    const bool prune = c.p.pass == 0 && c.res_len >= ef && c.res_len > 0 && !(c.res[c.res_len - 1] >> 63);
+    const uint32_t mb = prune ? (uint32_t)(c.res[c.res_len - 1] >> 32) : 0xffffffffu;
+    const bool qhas = u.acc && !u.qskip && !(prune && !(u.bits >> 31) && u.bits > mb);
+    const int mq = __popc(__ballot_sync(FULL, qhas));
+    if (c.q_len + mq > c.q_cap) {
+        int d0 = 0;
+        if (prune) {
+            for (int i = lane; i < c.q_len; i += 32) d0 += (uint32_t)(c.que[i] >> 32) > mb;
+            d0 = __reduce_add_sync(FULL, d0);
+        }
+        if (c.q_len + mq - d0 > c.q_cap) { c.overflow = true; return; }  // would have to drop a live entry
+    }
+    if (mq || prune)
+        c.q_len = merge_batch<true, true, MERGE_TILES>(c.que, c.q_len, qhas, ((u64)u.bits << 32) | (uint32_t)(~u.s), c.q_cap, mb);
 }
 
 // Visitor::visit — reader.rs:301-369 — and, with `linear`, the candidate loop of brute_force_search
 // (reader.rs:683-705).  Entry points: `eps` (n_eps slots in global memory) or `single`.
-// One loop feeds process_chunk: first the entry points (or the linear-scan candidates), then one chunk per
-// expansion — layer 0 reads the fixed-stride adjacency line (the line of the most likely next pop is requested
-// ahead), the other layers and irregular layer-0 graphs walk the CSR lists.
+//
+// One loop, one copy of the gather / distance / merge code.  Each iteration handles one chunk of <= 32 points:
+// first the entry points (or the linear-scan candidates), then one chunk per expansion — layer 0 reads the
+// fixed-stride adjacency line (the line of the most likely next pop is requested ahead), the other layers and
+// irregular layer-0 graphs walk the CSR lists.
+//
+// The heap update of a chunk is DEFERRED into the next iteration (layer 0, pass 0): the node popped next is decided
+// first — it is the smallest of (queue top, points the pending chunk accepted), and it is certain to be popped when
+// its distance does not exceed a lower bound of the next f_max (the result-set entry that survives whatever the
+// pending chunk evicts).  Its adjacency load and its visited-set atomics are then issued around the two merge
+// stages, which hide their latency.  When the bound does not settle it, the pending update is applied first and
+// the reference's order is followed literally.
 template <int KIND>
 __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_eps, uint32_t single, uint32_t level, int ef, bool filt, bool linear) {
     const DevIndex& ix = c.p.ix;
     const int lane = lane_id();
     const int l01 = level ? 0 : 1;
+    const u64 NONE = ~0ull;
     c.res_len = 0;
     c.q_len = 0;
     c.cur_dist = c.cur_exp = c.cur_deg = 0;
@@ -381,58 +378,152 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
     const uint32_t* off = ix.off[level];
     const uint32_t* nbr = ix.nbr[level];
     const uint32_t* nbrx = level == 0 ? ix.nbr0x : nullptr;
+    const bool defer = nbrx && c.p.pass == 0 && c.p.defer;
     uint32_t spec_cs = 0xffffffffu, spec_adj = 0xffffffffu;  // adjacency line requested ahead of its pop
     uint32_t csr_pos = 0, csr_end = 0;                       // rest of the CSR list being expanded
     float f_max = FLT_MAX;
-    while (!c.overflow) {
+    bool pend = false;
+    ChunkUpdate u;
+    u.mode = CH_EP; u.acc = u.pf = u.qskip = u.seq_done = false; u.bits = u.s = 0;
+    for (;;) {
         int mode;
-        uint32_t s;
-        bool valid;
+        uint32_t s = 0, old = 0xffffffffu;
+        bool valid = false, vis_sent = false;
         PH_DECL
-        if (base0 < n_first) {
+        if (base0 < n_first && !c.overflow) {
+            if (pend) { heaps_stage_res(c, u, ef); heaps_stage_queue(c, u, ef); pend = false; if (c.overflow) break; }
             valid = base0 + lane < n_first;
             s = !valid ? 0 : (list ? __ldg(&list[base0 + lane]) : single);
             base0 += 32;
             mode = linear ? CH_LINEAR : CH_EP;
         } else {
-            if (linear) break;
             mode = CH_NBR;
-            if (csr_pos >= csr_end) {
-                if (c.q_len == 0) break;
-                u64 top = c.que[c.q_len - 1];
-                float f = key_dist(top);
-                f_max = c.res_len ? key_dist(c.res[c.res_len - 1]) : FLT_MAX;
-                if (f > f_max) break;
-                c.q_len--;
-                uint32_t cs = ~(uint32_t)top;
-                c.cur_exp += 1;
-                TR(c, TR_POP)
-                if (nbrx) {
-                    s = (cs == spec_cs) ? spec_adj : __ldg(&nbrx[(size_t)cs * FIXED_DEG + lane]);
-                    // the entry now on top of the queue is popped next unless one of cs's neighbours beats it
-                    if (c.q_len > 0) {
-                        spec_cs = ~(uint32_t)c.que[c.q_len - 1];
-                        spec_adj = __ldg(&nbrx[(size_t)spec_cs * FIXED_DEG + lane]);
-                    } else {
-                        spec_cs = 0xffffffffu;
+            bool have = false;
+            if (pend && defer && csr_pos >= csr_end) {
+                // ---- decide the next pop before the pending update is applied ----
+                const u64 qk = u.acc ? (((u64)u.bits << 32) | (uint32_t)(~u.s)) : NONE;
+                const u64 cand_new = warp_min_u64(qk);
+                const u64 cand_old = c.q_len ? c.que[c.q_len - 1] : NONE;
+                const u64 nx = cand_new < cand_old ? cand_new : cand_old;
+                if (nx != NONE) {
+                    const int m_res = __popc(__ballot_sync(FULL, u.acc && u.pf));
+                    const int target = (u.mode == CH_EP || c.res_len > ef) ? c.res_len + m_res : min(ef, c.res_len + m_res);
+                    const int idx = target - 1 - m_res;  // the largest old entry that survives the pending evictions
+                    float bound = 0.0f;
+                    bool known = false;
+                    if (target == 0) { bound = FLT_MAX; known = true; }        // result set stays empty: f_max = f32::MAX
+                    else if (idx >= 0) { bound = key_dist(c.res[idx]); known = true; }
+                    if (known && !(key_dist(nx) > bound)) {
+                        const bool from_old = cand_old < cand_new;
+                        if (from_old) c.q_len--;
+                        u.qskip = !from_old && qk == nx;
+                        const uint32_t cs = ~(uint32_t)nx;
+                        c.cur_exp += 1;
+                        TR(c, TR_POP)
+                        uint32_t a = (cs == spec_cs) ? spec_adj : __ldg(&nbrx[(size_t)cs * FIXED_DEG + lane]);
+                        heaps_stage_res(c, u, ef);                 // ... while the adjacency line is on its way
+                        valid = a != 0xffffffffu;
+                        s = valid ? a : 0;
+                        old = vis_issue(c, s, valid);
+                        vis_sent = true;
+                        heaps_stage_queue(c, u, ef);               // ... while the visited-set atomics are on their way
+                        pend = false;
+                        if (l01) PH_ADD(c, PH_HEAP)
+                        TR(c, TR_HEAP)
+                        f_max = c.res_len ? key_dist(c.res[c.res_len - 1]) : FLT_MAX;  // what the reference reads at this pop
+                        have = true;
+                        if (!c.overflow && c.q_len > 0) {          // the line of the pop after this one
+                            spec_cs = ~(uint32_t)c.que[c.q_len - 1];
+                            spec_adj = __ldg(&nbrx[(size_t)spec_cs * FIXED_DEG + lane]);
+                        } else {
+                            spec_cs = 0xffffffffu;
+                        }
                     }
-                } else {
-                    csr_pos = __ldg(&off[cs]);
-                    csr_end = __ldg(&off[cs + 1]);
-                    if (csr_pos >= csr_end) continue;
                 }
             }
-            if (!nbrx) {
-                s = csr_pos + lane < csr_end ? __ldg(&nbr[csr_pos + lane]) : 0xffffffffu;
-                csr_pos += 32;
+            if (!have) {
+                if (pend) {
+                    heaps_stage_res(c, u, ef);
+                    heaps_stage_queue(c, u, ef);
+                    pend = false;
+                    if (l01) PH_ADD(c, PH_HEAP)
+                    TR(c, TR_HEAP)
+                }
+                if (c.overflow || linear) break;
+                if (csr_pos >= csr_end) {
+                    if (c.q_len == 0) break;
+                    u64 top = c.que[c.q_len - 1];
+                    float f = key_dist(top);
+                    f_max = c.res_len ? key_dist(c.res[c.res_len - 1]) : FLT_MAX;
+                    if (f > f_max) break;
+                    c.q_len--;
+                    uint32_t cs = ~(uint32_t)top;
+                    c.cur_exp += 1;
+                    TR(c, TR_POP)
+                    if (nbrx) {
+                        s = (cs == spec_cs) ? spec_adj : __ldg(&nbrx[(size_t)cs * FIXED_DEG + lane]);
+                        // the entry now on top of the queue is popped next unless one of cs's neighbours beats it
+                        if (c.q_len > 0) {
+                            spec_cs = ~(uint32_t)c.que[c.q_len - 1];
+                            spec_adj = __ldg(&nbrx[(size_t)spec_cs * FIXED_DEG + lane]);
+                        } else {
+                            spec_cs = 0xffffffffu;
+                        }
+                    } else {
+                        csr_pos = __ldg(&off[cs]);
+                        csr_end = __ldg(&off[cs + 1]);
+                        if (csr_pos >= csr_end) continue;
+                    }
+                }
+                if (!nbrx) {
+                    s = csr_pos + lane < csr_end ? __ldg(&nbr[csr_pos + lane]) : 0xffffffffu;
+                    csr_pos += 32;
+                }
+                valid = s != 0xffffffffu;
+                if (!valid) s = 0;
             }
-            valid = s != 0xffffffffu;
-            if (!valid) s = 0;
             c.cur_deg += __popc(__ballot_sync(FULL, valid));
             if (l01) PH_ADD(c, PH_ADJ)
             TR(c, TR_ADJ)
         }
-        process_chunk<KIND>(c, mode, s, valid, f_max, ef, filt, l01);
+        // ---- visited filter ----
+        bool live = valid;
+        if (mode != CH_LINEAR) {
+            if (!vis_sent) old = vis_issue(c, s, valid);
+            bool fresh = vis_finish(c, s, valid, old);           // `path.insert(..)`
+            if (mode == CH_NBR) live = fresh;                      // `if !path.insert(point) { continue }`; an ep's result is ignored
+        }
+        if (c.overflow) break;                                     // (a deferred merge ran out of room)
+        const unsigned lm = __ballot_sync(FULL, live);
+        if (l01) PH_ADD(c, PH_VIS)
+        TR(c, TR_VIS)
+        if (!lm) continue;
+        c.cur_dist += __popc(lm);
+        // ---- gather + distances ----
+        RowsInFlight rf;
+        rows_begin<KIND>(c, lm, s, rf);
+        TR(c, TR_POSTED)
+        const float dist = rows_finish<KIND>(c, rf, s);
+        const uint32_t bits = __float_as_uint(dist);
+        if (l01) PH_ADD(c, PH_ROWS)
+        if (mode != CH_LINEAR && c.p.pass == 0 && __ballot_sync(FULL, live && (bits >> 31))) { c.overflow = true; break; }
+        // ---- which points are accepted, and which of those may enter the result set (reader.rs:322,353,355-359) ----
+        const bool pf = live && passes_filter(c, s, filt);
+        bool acc = live;
+        if (mode == CH_NBR) {
+            // `res.len() < self.ef || dist < f_max` with live len and stale f_max (reader.rs:353): the first
+            // ef - len filter-passing points in ascending order are taken unconditionally.
+            unsigned pfm = __ballot_sync(FULL, pf);
+            int before = __popc(pfm & ((1u << lane) - 1));
+            bool fill = (c.res_len + before) < ef;
+            acc = live && (fill || dist < f_max);
+            // an accepted point that beats the queue's current best is expanded very soon: start pulling its adjacency line
+#ifndef HB_NO_ADJ_PREFETCH
+            if (nbrx && acc && (c.q_len == 0 || bits <= (uint32_t)(c.que[c.q_len - 1] >> 32))) prefetch_l2(nbrx + (size_t)s * FIXED_DEG);
+#endif
+        }
+        u.mode = mode; u.acc = acc; u.pf = pf; u.qskip = false; u.bits = bits; u.s = s;
+        pend = true;
     }
     if (level) { c.n_dist_up += c.cur_dist; c.n_exp_up += c.cur_exp; c.n_deg_up += c.cur_deg; }
     else { c.n_dist_l0 += c.cur_dist; c.n_exp_l0 += c.cur_exp; c.n_deg_l0 += c.cur_deg; }

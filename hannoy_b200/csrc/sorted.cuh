@@ -73,10 +73,14 @@ __device__ __forceinline__ void topk_insert(u64* a, int& len, int cap, u64 key) 
 //   drop_above (TRIM only) old entries whose distance bits exceed it are dropped: they sit at the front of a
 //              descending array
 //   keep       final length is capped to `keep` (the entries that sort last are dropped)
-// Needs len <= 32 * MAX_TILES.  Returns the new length.  Out of line on purpose: one copy per heap kind keeps the
-// search kernel's hot loop small (instruction cache), and the arguments are plain values.
+// Needs len <= 32 * MAX_TILES.  Returns the new length.
+#ifdef HB_MERGE_NOINLINE
+#define HB_MERGE_INLINE __noinline__
+#else
+#define HB_MERGE_INLINE __forceinline__
+#endif
 template <bool DESC, bool TRIM, int MAX_TILES>
-__device__ __noinline__ int merge_batch(u64* a, int len, bool has, u64 key, int keep, uint32_t drop_above) {
+__device__ HB_MERGE_INLINE int merge_batch(u64* a, int len, bool has, u64 key, int keep, uint32_t drop_above) {
     const int lane = lane_id();
     const unsigned hm = __ballot_sync(FULL, has);
     int pos = 0;
