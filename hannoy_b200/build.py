@@ -1,8 +1,9 @@
 """Builds libhannoy_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo).
 
-`python -m hannoy_b200.build [--force] [-v] [--variant phases]`; the `phases` variant (dev only) adds
--DHB_PHASES (per-phase cycle counters in the search kernel) and is written to libhannoy_b200_phases.so,
-loaded instead of the product library when HB_LIB_VARIANT=phases.
+`python -m hannoy_b200.build [--force] [-v] [--variant NAME]`; variants are dev builds written to
+libhannoy_b200_NAME.so and loaded instead of the product library when HB_LIB_VARIANT=NAME: `phases` (-DHB_PHASES:
+per-phase cycle counters in the search kernel), `trace` (-DHB_TRACE: event trace of one warp), `rg2` (rows reduced
+two at a time instead of four).
 """
 import os
 import subprocess
@@ -20,8 +21,7 @@ FLAGS = [
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false", "-split-compile", "0",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function",
 ]
-VARIANTS = {"": [], "phases": ["-DHB_PHASES"], "rg2": ["-DHB_ROW_GROUP=2"], "rg2phases": ["-DHB_ROW_GROUP=2", "-DHB_PHASES"],
-            "trace": ["-DHB_TRACE"], "mni": ["-DHB_MERGE_NOINLINE"], "nopf": ["-DHB_NO_ADJ_PREFETCH"], "rg2trace": ["-DHB_ROW_GROUP=2", "-DHB_TRACE"], "rg1": ["-DHB_ROW_GROUP=1"], "rg1b4": ["-DHB_ROW_GROUP=1", "-DHB_MIN_BLOCKS_F32=4"], "rg2b4": ["-DHB_ROW_GROUP=2", "-DHB_MIN_BLOCKS_F32=4"]}
+VARIANTS = {"": [], "phases": ["-DHB_PHASES"], "trace": ["-DHB_TRACE"], "rg2": ["-DHB_ROW_GROUP=2"]}
 
 
 def out_path(variant=""):

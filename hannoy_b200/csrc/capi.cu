@@ -392,8 +392,10 @@ static hb_status run_search(const hb_index* ix, Workspace* w, SearchParams base,
     base.q_smem_bytes = (d.row_stride + 15) & ~15u;
     base.defer = tunable("defer", 1);
     const uint32_t ef0 = std::max(base.ef_raw, base.count);
-    if (d.kind == KIND_F32_WARP) {
-        // rows in flight per warp: as many as fit the ring budget, in whole reduction groups
+    if (d.kind == KIND_F32_WARP && d.row_stride >= (uint32_t)tunable("ring_min_row", 0)) {
+        // rows in flight per warp: as many as fit the ring budget, in whole reduction groups (512-byte rows: the
+        // whole neighbour list of an expansion in one shot).  "ring_min_row" routes shorter rows to the plain-load
+        // gather (search.cu KIND_F32_DIRECT) instead; measured slower on C2 (1.57M vs 1.84M QPS), so off by default.
         uint32_t budget = (uint32_t)std::max(0, tunable("ring_bytes", 12288));
         uint32_t slots = budget / d.row_stride / ROW_GROUP * ROW_GROUP;
         slots = std::max<uint32_t>(ROW_GROUP, std::min<uint32_t>(slots, 32));

@@ -107,18 +107,18 @@ __device__ __forceinline__ void warp_rows_raw(const DevIndex& ix, const float* q
     }
 }
 
-// Same arithmetic for a group of R rows staged in shared memory, with the R horizontal sums folded into one
-// butterfly: at the xor-4 step half of the lanes keep rows {0,1} and the other half rows {2,3} (each lane sends
-// the partial sums it drops and receives the ones it keeps), at the xor-2 step one row is kept, so 4 rows cost
-// 4 shuffles instead of 12.  Every individual addition is one the AVX code performs (x[l+4]+x[l]; r0+r2, r1+r3;
-// s0+s1; ((h1+h2)+h3)+h4 — simple_avx.rs:8-13,55-58), fp32 addition being commutative, so the sums are bit-identical.
-// Returns row r's raw sum on the lanes l with group_owner<R>(r) == l & 7 (all four 8-lane groups).
+// Same arithmetic for a group of R rows (staged in shared memory by the bulk-copy ring, or read straight from global
+// memory with 128-bit loads), with the R horizontal sums folded into one butterfly: at each xor step a lane keeps
+// half of the rows it still holds (it sends the partial sums it drops and receives the ones it keeps), so 8 rows
+// cost 4+2+1 shuffles instead of 24.  Every individual addition is one the AVX code performs (x[l+4]+x[l]; r0+r2,
+// r1+r3; s0+s1; ((h1+h2)+h3)+h4 — simple_avx.rs:8-13,55-58), fp32 addition being commutative, so the sums are
+// bit-identical.  Returns row r's raw sum on the lanes l with (l & 7) == group_owner<R>(r) (all four 8-lane groups).
 template <int R>
-__device__ __forceinline__ int group_owner(int r) { return R == 4 ? 2 * r : (R == 2 ? 4 * r : 0); }
+__device__ __forceinline__ int group_owner(int r) { return r * (8 / R); }
 
-template <int R, bool DOT>
+template <int R, bool DOT, bool ROWS_SMEM>
 __device__ __forceinline__ float warp_rows_group(const DevIndex& ix, const float* qs, const uint8_t* const (&rowp)[R]) {
-    static_assert(R == 1 || R == 2 || R == 4, "row group must be 1, 2 or 4");
+    static_assert(R == 1 || R == 2 || R == 4 || R == 8, "row group must be 1, 2, 4 or 8");
     const int lane = lane_id();
     float acc[R];
 #pragma unroll
@@ -128,16 +128,19 @@ __device__ __forceinline__ float warp_rows_group(const DevIndex& ix, const float
     for (uint32_t c = 0; c < ix.n_chunks; ++c) {
         float4 v[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = *(reinterpret_cast<const float4*>(rowp[r]) + c * 32 + lane);
+        for (int r = 0; r < R; ++r) {
+            const float4* p4 = reinterpret_cast<const float4*>(rowp[r]) + c * 32 + lane;
+            v[r] = ROWS_SMEM ? *p4 : __ldg(p4);
+        }
         float4 qv = q4[c * 32 + lane];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            if (DOT) {
+            if (DOT) {  // dot_similarity_avx: acc = fma(a, b, acc)  (simple_avx.rs:85-97)
                 acc[r] = fmaf(qv.x, v[r].x, acc[r]);
                 acc[r] = fmaf(qv.y, v[r].y, acc[r]);
                 acc[r] = fmaf(qv.z, v[r].z, acc[r]);
                 acc[r] = fmaf(qv.w, v[r].w, acc[r]);
-            } else {
+            } else {  // euclid_similarity_avx: d = a - b; acc = fma(d, d, acc)  (simple_avx.rs:33-53)
                 float d0 = __fsub_rn(qv.x, v[r].x), d1 = __fsub_rn(qv.y, v[r].y);
                 float d2 = __fsub_rn(qv.z, v[r].z), d3 = __fsub_rn(qv.w, v[r].w);
                 acc[r] = fmaf(d0, d0, acc[r]);
@@ -147,43 +150,41 @@ __device__ __forceinline__ float warp_rows_group(const DevIndex& ix, const float
             }
         }
     }
-    float k;
-    int my_r;  // the row whose sum this lane ends up holding
-    if (R == 4) {
-        const bool hi4 = lane & 4, hi2 = lane & 2;
-        float k0 = hi4 ? acc[R > 2 ? 2 : 0] : acc[0], k1 = hi4 ? acc[R > 3 ? 3 : 0] : acc[R > 1 ? 1 : 0];
-        float s0 = hi4 ? acc[0] : acc[R > 2 ? 2 : 0], s1 = hi4 ? acc[R > 1 ? 1 : 0] : acc[R > 3 ? 3 : 0];
-        k0 = __fadd_rn(k0, __shfl_xor_sync(FULL, s0, 4));
-        k1 = __fadd_rn(k1, __shfl_xor_sync(FULL, s1, 4));
-        k = hi2 ? k1 : k0;
-        float snd = hi2 ? k0 : k1;
-        k = __fadd_rn(k, __shfl_xor_sync(FULL, snd, 2));
-        my_r = (lane >> 1) & 3;
+    // fold: after the xor-4 / xor-2 / xor-1 steps lane l holds the 8-lane-group sum of row ((l & 7) * R) >> 3
+    // (constant indices only: the partial sums must stay in registers)
+#define HB_FOLD(i, j, step) { const bool hi_ = lane & step; float keep_ = hi_ ? acc[j] : acc[i]; float send_ = hi_ ? acc[i] : acc[j]; \
+                              acc[i] = __fadd_rn(keep_, __shfl_xor_sync(FULL, send_, step)); }
+#define HB_PLAIN(step) { acc[0] = __fadd_rn(acc[0], __shfl_xor_sync(FULL, acc[0], step)); }
+    if (R == 8) {
+        HB_FOLD(0, R > 4 ? 4 : 0, 4) HB_FOLD(R > 1 ? 1 : 0, R > 5 ? 5 : 0, 4) HB_FOLD(R > 2 ? 2 : 0, R > 6 ? 6 : 0, 4) HB_FOLD(R > 3 ? 3 : 0, R > 7 ? 7 : 0, 4)
+        HB_FOLD(0, R > 2 ? 2 : 0, 2) HB_FOLD(R > 1 ? 1 : 0, R > 3 ? 3 : 0, 2)
+        HB_FOLD(0, R > 1 ? 1 : 0, 1)
+    } else if (R == 4) {
+        HB_FOLD(0, R > 2 ? 2 : 0, 4) HB_FOLD(R > 1 ? 1 : 0, R > 3 ? 3 : 0, 4)
+        HB_FOLD(0, R > 1 ? 1 : 0, 2)
+        HB_PLAIN(1)
     } else if (R == 2) {
-        const bool hi4 = lane & 4;
-        k = hi4 ? acc[R > 1 ? 1 : 0] : acc[0];
-        float snd = hi4 ? acc[0] : acc[R > 1 ? 1 : 0];
-        k = __fadd_rn(k, __shfl_xor_sync(FULL, snd, 4));
-        k = __fadd_rn(k, __shfl_xor_sync(FULL, k, 2));
-        my_r = (lane >> 2) & 1;
+        HB_FOLD(0, R > 1 ? 1 : 0, 4)
+        HB_PLAIN(2) HB_PLAIN(1)
     } else {
-        k = __fadd_rn(acc[0], __shfl_xor_sync(FULL, acc[0], 4));
-        k = __fadd_rn(k, __shfl_xor_sync(FULL, k, 2));
-        my_r = 0;
+        HB_PLAIN(4) HB_PLAIN(2) HB_PLAIN(1)
     }
-    k = __fadd_rn(k, __shfl_xor_sync(FULL, k, 1));
+#undef HB_FOLD
+#undef HB_PLAIN
+    const float k = acc[0];
     const int sub = lane & 7;
     float h1 = __shfl_sync(FULL, k, sub), h2 = __shfl_sync(FULL, k, 8 + sub);
     float h3 = __shfl_sync(FULL, k, 16 + sub), h4 = __shfl_sync(FULL, k, 24 + sub);
     float res = __fadd_rn(__fadd_rn(__fadd_rn(h1, h2), h3), h4);
     if (ix.tail) {  // scalar tail, n % 32 elements, unfused (simple_avx.rs:59-63,104-108), on the lanes that hold the row
+        const int my_r = (sub * R) >> 3;
         const uint8_t* rp = rowp[0];
 #pragma unroll
         for (int r = 1; r < R; ++r) if (my_r == r) rp = rowp[r];
         const float* rt = reinterpret_cast<const float*>(rp) + ix.tail_off;
         const float* qt = qs + ix.tail_off;
         for (uint32_t e = 0; e < ix.tail; ++e) {
-            float a = qt[e], b = rt[e];
+            float a = qt[e], b = ROWS_SMEM ? rt[e] : __ldg(rt + e);
             if (DOT) res = __fadd_rn(res, __fmul_rn(a, b));
             else { float d = __fsub_rn(a, b); res = __fadd_rn(res, __fmul_rn(d, d)); }
         }

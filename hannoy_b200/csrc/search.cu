@@ -22,11 +22,24 @@
 #include "ring.cuh"
 #include "sorted.cuh"
 
+#ifndef HB_DIRECT_R
+#define HB_DIRECT_R 8  // rows per group of the direct gather when a row is one 128-float chunk
+#endif
+#ifndef HB_MIN_BLOCKS_DIRECT
+#define HB_MIN_BLOCKS_DIRECT 4
+#endif
 #ifndef HB_MIN_BLOCKS_F32
 #define HB_MIN_BLOCKS_F32 3  // resident CTAs per SM the f32 kernel is compiled for (register budget)
 #endif
 
 namespace hb {
+
+// Kernel variants: the three row kinds of common.h, plus KIND_F32_WARP rows gathered with plain 128-bit loads instead
+// of the bulk-copy ring: for rows too long to stage in shared memory (and, optionally, for short rows — the
+// bulk-copy engine tops out near one copy per ~72 cycles per SM, tools/gather_bench.cu).  8 (one-chunk rows) or 4
+// rows go through registers at a time.
+constexpr int KIND_F32_DIRECT = 3;
+__host__ __device__ constexpr bool is_f32_warp(int kind) { return kind == KIND_F32_WARP || kind == KIND_F32_DIRECT; }
 
 // Optional phase timers (build with -DHB_PHASES; dev only): cycles per phase summed over all queries.
 __device__ unsigned long long g_phase[16];
@@ -217,10 +230,34 @@ __device__ __forceinline__ void rows_begin(Ctx& c, unsigned mask, uint32_t s, Ro
         // lanes that own them.
         if (rf.rank < (int)c.ring.slots) c.ring.post(rf.rank, rf.grow, ix.row_stride);
         if (ix.metric == HB_COSINE) rf.in = __ldg(&ix.hdr[s]);
+    } else if (KIND == KIND_F32_DIRECT) {
+        if (ix.metric == HB_COSINE) rf.in = __ldg(&ix.hdr[s]);
     } else {
         for (uint32_t o = 0; o < ix.row_stride; o += 128) prefetch_l2(rf.grow + o);
         if (ix.metric == HB_COSINE || ix.metric == HB_BQ_COSINE) rf.in = __ldg(&ix.hdr[s]);
     }
+}
+
+// R live rows at a time straight from global memory: lane j loads float4 j of every chunk of each row (coalesced
+// 512-byte lines), all R x chunks loads of a group are independent and in flight together.
+template <int R>
+__device__ __forceinline__ float direct_rows(Ctx& c, const RowsInFlight& rf, uint32_t s) {
+    const DevIndex& ix = c.p.ix;
+    float myraw = 0.0f;
+    for (int r0 = 0; r0 < rf.n_live; r0 += R) {
+        const int g = min(R, rf.n_live - r0);
+        const uint8_t* rowp[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int owner = __fns(rf.mask, 0, r0 + (r < g ? r : 0) + 1);  // lane of the (r0 + r)-th live row
+            rowp[r] = ix.rows + (size_t)__shfl_sync(FULL, s, owner) * ix.row_stride;
+        }
+        const float red = (ix.metric == HB_COSINE) ? warp_rows_group<R, true, false>(ix, c.qs, rowp) : warp_rows_group<R, false, false>(ix, c.qs, rowp);
+        const int mr = rf.rank - r0;
+        const float got = __shfl_sync(FULL, red, group_owner<R>(mr >= 0 && mr < R ? mr : 0));
+        if (rf.has && mr >= 0 && mr < g) myraw = got;
+    }
+    return myraw;
 }
 
 template <int KIND>
@@ -228,25 +265,11 @@ __device__ __forceinline__ float rows_finish(Ctx& c, const RowsInFlight& rf, uin
     const DevIndex& ix = c.p.ix;
     const int lane = lane_id();
     float mine = 0.0f;
-    if (KIND == KIND_F32_WARP && c.ring.slots == 0) {
-        // rows too long for the shared-memory ring: 4 rows at a time straight from global memory
-        unsigned m = rf.mask;
-        while (m) {
-            int l[4];
-            const uint8_t* rowp[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if (m) { l[r] = __ffs(m) - 1; m &= m - 1; } else l[r] = -1;
-                uint32_t sl = __shfl_sync(FULL, s, l[r] < 0 ? l[0] : l[r]);
-                rowp[r] = ix.rows + (size_t)sl * ix.row_stride;
-            }
-            float raw[4];
-            if (ix.metric == HB_COSINE) warp_rows_raw<4, true, false>(ix, c.qs, rowp, raw);
-            else warp_rows_raw<4, false, false>(ix, c.qs, rowp, raw);
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-                if (lane == l[r]) mine = finish_f32(ix.metric, raw[r], c.qn, rf.in);
-        }
+    if (KIND == KIND_F32_DIRECT) {
+        float myraw = 0.0f;
+        if (ix.n_chunks <= 1) myraw = direct_rows<HB_DIRECT_R>(c, rf, s);
+        else myraw = direct_rows<4>(c, rf, s);
+        if (rf.has) mine = finish_f32(ix.metric, myraw, c.qn, rf.in);
     } else if (KIND == KIND_F32_WARP) {
         // slot group g is re-posted as soon as its ROW_GROUP rows were consumed
         const int S = (int)c.ring.slots;
@@ -261,7 +284,7 @@ __device__ __forceinline__ float rows_finish(Ctx& c, const RowsInFlight& rf, uin
                 rowp[r] = c.ring.ptr + (size_t)(slot0 + (r < g ? r : 0)) * c.ring.stride;
             }
             // row r's sum comes back on lane group_owner(r); the lane that owns the row picks it up
-            float red = (ix.metric == HB_COSINE) ? warp_rows_group<ROW_GROUP, true>(ix, c.qs, rowp) : warp_rows_group<ROW_GROUP, false>(ix, c.qs, rowp);
+            float red = (ix.metric == HB_COSINE) ? warp_rows_group<ROW_GROUP, true, true>(ix, c.qs, rowp) : warp_rows_group<ROW_GROUP, false, true>(ix, c.qs, rowp);
             __syncwarp();  // every lane has read the group's slots: they may be overwritten
             const int nxt = rf.rank - r0 - S;
             if (rf.has && nxt >= 0 && nxt < g) c.ring.post(slot0 + nxt, rf.grow, ix.row_stride);
@@ -545,7 +568,7 @@ __device__ void stage_query(Ctx& c, float* qs, uint64_t qi) {
         for (uint32_t i = lane; i < words16; i += 32) q16[i] = make_uint4(0, 0, 0, 0);
         __syncwarp();
         const float* src = c.p.q + qi * ix.dims;
-        if (KIND == KIND_F32_WARP) {
+        if (is_f32_warp(KIND)) {
             uint32_t main = ix.dims - ix.tail;
             for (uint32_t e = lane; e < ix.dims; e += 32) {
                 float v = __ldg(src + e);
@@ -578,7 +601,7 @@ __device__ void stage_query(Ctx& c, float* qs, uint64_t qi) {
     float qn = 0.0f;
     if (ix.metric == HB_COSINE) {
         float dot;
-        if (KIND == KIND_F32_WARP) {
+        if (is_f32_warp(KIND)) {
             // dot(q, q) in the same lane order: the query doubles as the "row" (shared-memory reads)
             float acc = 0.0f;
             const float4* q4 = reinterpret_cast<const float4*>(qs);
@@ -776,7 +799,7 @@ __device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64*
 
 // Shared memory of one warp: [row ring][ring barriers][query][heaps (pass 0 only)].
 template <int KIND>
-__global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, KIND == KIND_F32_WARP ? HB_MIN_BLOCKS_F32 : 4) hnsw_search_kernel(const __grid_constant__ SearchParams p) {
+__global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, KIND == KIND_F32_WARP ? HB_MIN_BLOCKS_F32 : (KIND == KIND_F32_DIRECT ? HB_MIN_BLOCKS_DIRECT : 4)) hnsw_search_kernel(const __grid_constant__ SearchParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp_in_block = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
@@ -854,9 +877,12 @@ size_t search_smem_per_warp(const SearchParams& p) {
 }
 
 typedef void (*search_kernel_t)(const SearchParams);
+// the kernel variant a call runs: f32 warp rows without a ring are gathered directly
+static int variant_of(const SearchParams& p) { return (p.ix.kind == KIND_F32_WARP && p.ring_slots == 0) ? KIND_F32_DIRECT : p.ix.kind; }
 static search_kernel_t kernel_for(int kind) {
     switch (kind) {
         case KIND_F32_WARP: return hnsw_search_kernel<KIND_F32_WARP>;
+        case KIND_F32_DIRECT: return hnsw_search_kernel<KIND_F32_DIRECT>;
         case KIND_F32_LANE: return hnsw_search_kernel<KIND_F32_LANE>;
         default: return hnsw_search_kernel<KIND_BIN>;
     }
@@ -864,7 +890,7 @@ static search_kernel_t kernel_for(int kind) {
 static void set_kernel_attrs() {
     static bool attr_set = false;
     if (!attr_set) {
-        for (int k = 0; k < 3; ++k)
+        for (int k = 0; k < 4; ++k)
             cudaFuncSetAttribute(kernel_for(k), cudaFuncAttributeMaxDynamicSharedMemorySize, SEARCH_MAX_SMEM);
         attr_set = true;
     }
@@ -875,7 +901,7 @@ int search_blocks_per_sm(const SearchParams& p) {
     int nb = 0;
     size_t smem = search_smem_per_warp(p) * SEARCH_WARPS_PER_BLOCK;
     if (smem > (size_t)SEARCH_MAX_SMEM) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel_for(p.ix.kind), SEARCH_WARPS_PER_BLOCK * 32, smem) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel_for(variant_of(p)), SEARCH_WARPS_PER_BLOCK * 32, smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
@@ -895,7 +921,7 @@ hb_status launch_search(const SearchParams& fast, const SearchParams& slow, int 
         uint64_t need = ((uint64_t)fast.n_work + wpb - 1) / wpb;
         int blocks = (uint64_t)blocks_fast > need ? (int)need : blocks_fast;
         if (blocks < 1) blocks = 1;
-        kernel_for(fast.ix.kind)<<<blocks, wpb * 32, smem, stream>>>(fast);
+        kernel_for(variant_of(fast))<<<blocks, wpb * 32, smem, stream>>>(fast);
         ++g_launches;
     } else {
         uint32_t n = fast.n_work;
@@ -903,7 +929,7 @@ hb_status launch_search(const SearchParams& fast, const SearchParams& slow, int 
         ++g_launches;
     }
     size_t smem = search_smem_per_warp(slow) * wpb;
-    kernel_for(slow.ix.kind)<<<blocks_slow, wpb * 32, smem, stream>>>(slow);
+    kernel_for(variant_of(slow))<<<blocks_slow, wpb * 32, smem, stream>>>(slow);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("search launch failed: %s", cudaGetErrorString(e)); return HB_ECUDA; }
