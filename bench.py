@@ -361,15 +361,35 @@ def main():
         qb.by_vectors_raw(q_pinned)
     if use_dist:
         dist.barrier()
-    e2e_steps = max(3, min(args.steps, 10))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        out = qb.by_vectors_raw(q_pinned)
-    t_e2e = (time.perf_counter() - t0) / e2e_steps
+    e2e_steps = max(4, min(args.steps, 12)) // 2 * 2
+
+    def e2e_run(in_flight):
+        """`e2e_steps` batches through the host API with `in_flight` host threads submitting concurrently (the C-ABI
+        is thread-safe: every call takes its own workspace and stream, so one batch's copies and kernel tail overlap
+        the next batch's).  Returns seconds per batch."""
+        per = e2e_steps // in_flight
+        outs = [None] * in_flight
+
+        def worker(i):
+            qb_i = rd.nns(k).ef_search(ef_pick)
+            for _ in range(per):
+                outs[i] = qb_i.by_vectors_raw(q_pinned)
+
+        ths = [threading.Thread(target=worker, args=(i,)) for i in range(in_flight)]
+        t0 = time.perf_counter()
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        return (time.perf_counter() - t0) / (per * in_flight), outs[0]
+
+    e2e_run(2)  # warm the second workspace
+    t_serial, out = e2e_run(1)
+    t_e2e, out = e2e_run(2)
     if use_dist:
-        t = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
+        t = torch.tensor([t_e2e, t_serial], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
+        t_e2e, t_serial = float(t[0].item()), float(t[1].item())
     e2e_qps = nq * world / t_e2e
     h2d = q_host.nbytes
     d2h = out[0].nbytes + out[1].nbytes + out[2].nbytes
@@ -401,7 +421,9 @@ def main():
             "data": "synthetic", "config": dict(config, ef_search=ef_pick, recall_at_k=recall, recall_sweep=sweep,
                                                 parity_vs_oracle="bit-exact" if parity_ok else "MISMATCH"),
             "clocks": clocks,
-            "e2e": {"value": round(e2e_qps, 1), "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": round(e2e_qps, 1), "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "batches_in_flight": 2, "one_batch_at_a_time": round(nq * world / t_serial, 1),
+                    "note": "hb_search_by_vector on pinned host buffers; 2 host threads submit whole batches concurrently"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",

@@ -1,5 +1,6 @@
 // common.h — structures shared by the host side (snapshot.cpp, capi.cu) and the kernels.
 #pragma once
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
 #include <map>
@@ -176,7 +177,7 @@ int tunable(const char* key, int dflt);
 hb_status launch_exact_knn(const DevIndex& ix, const float* d_q, uint64_t nq, uint32_t k, uint32_t* d_ids, float* d_dist, void* stream);
 hb_status launch_merge_topk(const uint32_t* d_ids, const float* d_dist, uint32_t n_parts, uint64_t nq, uint32_t k,
                             uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len, void* stream);
-extern unsigned long long g_launches;
+extern std::atomic<unsigned long long> g_launches;
 void read_phases(unsigned long long* out);
 uint32_t read_trace(unsigned long long* out, uint32_t cap);
 }  // namespace hb

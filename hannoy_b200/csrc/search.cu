@@ -838,7 +838,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, KIND == KIND_F32_
     }
 }
 
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 
 // dev: read and reset the phase timers (all zero unless built with -DHB_PHASES)
 void read_phases(unsigned long long* out) {
