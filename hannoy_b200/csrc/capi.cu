@@ -263,6 +263,7 @@ static void free_workspace(Workspace* w) {
     cudaFree(w->visited); cudaFree(w->touched); cudaFree(w->work_counter); cudaFree(w->overflow_list);
     cudaFree(w->n_overflow); cudaFree(w->gheap); cudaFree(w->d_q); cudaFree(w->d_out); cudaFree(w->d_cand);
     if (w->stream) cudaStreamDestroy((cudaStream_t)w->stream);
+    if (w->busy) cudaEventDestroy((cudaEvent_t)w->busy);
     delete w;
 }
 
@@ -340,15 +341,28 @@ static hb_status make_workspace(hb_index* ix, Workspace** out) {
     cudaStream_t s;
     CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     w->stream = s;
+    cudaEvent_t ev;
+    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    w->busy = ev;
     *out = w;
     return HB_OK;
 }
 
-static hb_status acquire_ws(const hb_index* cix, Workspace** out) {
+static hb_status acquire_ws(const hb_index* cix, Workspace** out, void* for_stream = nullptr) {
     hb_index* ix = const_cast<hb_index*>(cix);
     {
+        // a workspace released by the device API may still be in use by a kernel on the caller's stream: take
+        // one whose `busy` event has fired, else make a new one
         std::lock_guard<std::mutex> g(ix->ws_mu);
-        if (!ix->ws_free.empty()) { *out = ix->ws_free.back(); ix->ws_free.pop_back(); return HB_OK; }
+        for (size_t i = ix->ws_free.size(); i-- > 0;) {
+            Workspace* w = ix->ws_free[i];
+            if (!w->async_used || (for_stream && w->last_stream == for_stream) || cudaEventQuery((cudaEvent_t)w->busy) == cudaSuccess) {
+                ix->ws_free.erase(ix->ws_free.begin() + i);
+                *out = w;
+                return HB_OK;
+            }
+            cudaGetLastError();  // cudaErrorNotReady is not sticky, but clear it
+        }
     }
     Workspace* w = nullptr;
     hb_status st = make_workspace(ix, &w);
@@ -520,6 +534,7 @@ static hb_status search_host(const hb_index* ix, const float* q, const uint32_t*
     if (out_ctr) cudaMemcpyAsync(out_ctr, p.out_ctr, ctr_b, cudaMemcpyDeviceToHost, stream);
     cudaError_t e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) { set_error("search failed: %s", cudaGetErrorString(e)); return fail(HB_ECUDA); }
+    w->async_used = false;  // drained
     release_ws(ix, w);
     return HB_OK;
 }
@@ -565,13 +580,16 @@ hb_status hb_search_by_vector_device(const hb_index* ix, const float* d_q, uint6
     }
     CUDA_TRY(cudaSetDevice(ix->device));
     Workspace* w = nullptr;
-    hb_status st = acquire_ws(ix, &w);
+    hb_status st = acquire_ws(ix, &w, stream ? stream : (void*)1);
     if (st != HB_OK) return st;
     SearchParams p;
     p.q = d_q; p.nq = nq; p.count = count; p.ef_raw = ef; p.mode = 0;
     p.out_ids = d_out_ids; p.out_dist = d_out_dist; p.out_len = d_out_len; p.out_ctr = d_out_counters;
     st = run_search(ix, w, p, stream);
-    // the workspace is only reusable once the stream has drained; the caller serialises calls on `stream`
+    // the workspace becomes reusable once everything enqueued so far on `stream` has run
+    cudaEventRecord((cudaEvent_t)w->busy, (cudaStream_t)stream);
+    w->last_stream = stream ? stream : (void*)1;  // (void*)1 stands for the legacy default stream
+    w->async_used = true;
     release_ws(ix, w);
     return st;
 }

@@ -113,6 +113,9 @@ struct Workspace {
     uint64_t gheap_entries_per_slot = 0;
     int slow_slots = 0;
     void* stream = nullptr;  // cudaStream_t owned by the workspace (host API)
+    void* busy = nullptr;    // cudaEvent_t: recorded behind the last asynchronous use (device API); reusable once it has fired
+    void* last_stream = nullptr;  // ... or at once by a call on the same stream (stream order)
+    bool async_used = false;
     // staging buffers for the host API (grown on demand)
     void* d_q = nullptr; size_t d_q_bytes = 0;
     void* d_out = nullptr; size_t d_out_bytes = 0;

@@ -124,3 +124,47 @@ def test_id_sharded_search_merge_on_one_device():
         assert gl[i] == len(keys)
         assert gi[i, :len(keys)].tolist() == [kk[1] for kk in keys], f"query {i}"
         assert gd[i, :len(keys)].tolist() == [kk[0] for kk in keys], f"query {i}"
+
+
+def test_concurrent_calls_threads_and_streams():
+    """`Reader: Send + Sync` (an hb_index is immutable after finalize): host calls from several threads and
+    device-resident calls on several streams may overlap; every call gets a private workspace."""
+    import threading
+    import torch
+    db, x = make_db("cosine", 4000, 96, seed=21, kind="clustered", n_threads=4)
+    rd = open_reader_arrays(db, "cosine")
+    qs = [make_vectors(700, 96, seed=100 + i, kind="clustered") for i in range(4)]
+    want = [db.search_by_vector(q, 10, ef=64, n_threads=4) for q in qs]
+    got = [None] * 4
+
+    def worker(i):
+        for _ in range(3):
+            got[i] = rd.nns(10).ef_search(64).by_vectors_raw(qs[i])
+
+    ths = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    for i in range(4):
+        assert_same(got[i], want[i], f"thread {i}")
+    # device-resident API on four streams, all in flight together
+    dev = torch.device("cuda", 0)
+    streams = [torch.cuda.Stream(dev) for _ in range(4)]
+    bufs = []
+    for i, st in enumerate(streams):
+        d_q = torch.from_numpy(qs[i]).to(dev)
+        d_ids = torch.empty((700, 10), dtype=torch.int32, device=dev)
+        d_dist = torch.empty((700, 10), dtype=torch.float32, device=dev)
+        d_len = torch.empty((700,), dtype=torch.int32, device=dev)
+        bufs.append((d_q, d_ids, d_dist, d_len))
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for i, st in enumerate(streams):
+            d_q, d_ids, d_dist, d_len = bufs[i]
+            rd.search_device(d_q.data_ptr(), 700, 10, 64, d_ids.data_ptr(), d_dist.data_ptr(), d_len.data_ptr(), None, st.cuda_stream)
+    torch.cuda.synchronize()
+    for i in range(4):
+        d_q, d_ids, d_dist, d_len = bufs[i]
+        g = (d_ids.cpu().numpy().view(np.uint32), d_dist.cpu().numpy(), d_len.cpu().numpy().view(np.uint32))
+        assert_same(g, want[i], f"stream {i}")
