@@ -23,6 +23,7 @@ EXPORTS = [
     "hb_index_max_level", "hb_index_version", "hb_index_item_ids", "hb_index_contains_item", "hb_index_item_vector",
     "hb_search_by_vector", "hb_search_by_item", "hb_search_by_vector_device", "hb_exact_knn", "hb_merge_topk_device",
     "hb_launch_count", "hb_last_error", "hb_tune", "hb_debug_phases", "hb_debug_trace",
+    "hb_shard_group_create", "hb_shard_group_connect", "hb_search_sharded_device", "hb_shard_group_free",
 ]
 
 
@@ -61,6 +62,10 @@ def lib():
         "hb_search_by_vector_device": (i32, [vp, vp, u64, u32, u32, vp, vp, vp, vp, vp]),
         "hb_exact_knn": (i32, [vp, vp, u64, u32, u32, vp, vp]),
         "hb_merge_topk_device": (i32, [i32, vp, vp, u32, u64, u32, vp, vp, vp, vp]),
+        "hb_shard_group_create": (i32, [i32, i32, i32, u64, u32, C.POINTER(vp), vp]),
+        "hb_shard_group_connect": (i32, [vp, vp]),
+        "hb_search_sharded_device": (i32, [vp, vp, vp, u64, u32, u32, vp, vp, vp, vp]),
+        "hb_shard_group_free": (None, [vp]),
         "hb_tune": (i32, [C.c_char_p, i32]), "hb_debug_phases": (None, [vp]), "hb_debug_trace": (u32, [vp, u32]), "hb_launch_count": (u64, []), "hb_last_error": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():

@@ -594,6 +594,110 @@ hb_status hb_search_by_vector_device(const hb_index* ix, const float* d_q, uint6
     return st;
 }
 
+// ---- id-sharded search with the all-gather fused into the search epilogue (peer memory over NVLink) ----------
+struct hb_shard_group {
+    int device = -1, n_shards = 0, rank = 0;
+    uint64_t nq_cap = 0;
+    uint32_t k_cap = 0;
+    void* local = nullptr;                 // this rank's exchange buffer (cudaMalloc, exported through CUDA IPC)
+    size_t bytes = 0, off_dist[2] = {0, 0}, off_ids[2] = {0, 0}, off_flags = 0;
+    void* peer_base[HB_MAX_SHARDS] = {};   // every shard's exchange buffer mapped here (own entry = local)
+    bool opened[HB_MAX_SHARDS] = {};
+    uint32_t** d_peer_flags = nullptr;     // device array of the peers' flag arrays
+    uint32_t epoch = 0;
+};
+
+hb_status hb_shard_group_create(int device, int n_shards, int rank, uint64_t nq_cap, uint32_t k_cap, hb_shard_group** out,
+                                uint8_t handle_out[64]) {
+    if (!out || !handle_out || n_shards < 1 || n_shards > HB_MAX_SHARDS || rank < 0 || rank >= n_shards) { set_error("bad shard group arguments"); return HB_EINVAL; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CUDA_TRY(cudaSetDevice(device));
+    hb_shard_group* g = new hb_shard_group();
+    g->device = device; g->n_shards = n_shards; g->rank = rank; g->nq_cap = nq_cap; g->k_cap = k_cap;
+    size_t part = ((size_t)n_shards * nq_cap * k_cap * 4 + 255) & ~(size_t)255;
+    g->off_ids[0] = 0; g->off_dist[0] = part; g->off_ids[1] = 2 * part; g->off_dist[1] = 3 * part;  // two epochs' buffers
+    g->off_flags = 4 * part;
+    g->bytes = g->off_flags + 256;
+    if (cudaMalloc(&g->local, g->bytes) != cudaSuccess) { delete g; set_error("cudaMalloc of the exchange buffer failed"); return HB_ENOMEM; }
+    cudaMemset(g->local, 0, g->bytes);
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, g->local) != cudaSuccess) { set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(cudaGetLastError())); cudaFree(g->local); delete g; return HB_ECUDA; }
+    std::memcpy(handle_out, &h, 64);
+    g->peer_base[rank] = g->local;
+    *out = g;
+    return HB_OK;
+}
+
+// `handles`: n_shards x 64 bytes, the handle every rank got from hb_shard_group_create, in rank order (exchange them
+// with any host-side all-gather).  Maps every peer's exchange buffer into this process.
+hb_status hb_shard_group_connect(hb_shard_group* g, const uint8_t* handles) {
+    if (!g || !handles) return HB_EINVAL;
+    CUDA_TRY(cudaSetDevice(g->device));
+    for (int r = 0; r < g->n_shards; ++r) {
+        if (r == g->rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + 64 * r, 64);
+        if (cudaIpcOpenMemHandle(&g->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            set_error("cudaIpcOpenMemHandle (shard %d) failed: %s", r, cudaGetErrorString(cudaGetLastError()));
+            return HB_ECUDA;
+        }
+        g->opened[r] = true;
+    }
+    std::vector<uint32_t*> flags(g->n_shards);
+    for (int r = 0; r < g->n_shards; ++r) flags[r] = (uint32_t*)((uint8_t*)g->peer_base[r] + g->off_flags);
+    CUDA_TRY(cudaMalloc(&g->d_peer_flags, sizeof(uint32_t*) * g->n_shards));
+    CUDA_TRY(cudaMemcpy(g->d_peer_flags, flags.data(), sizeof(uint32_t*) * g->n_shards, cudaMemcpyHostToDevice));
+    return HB_OK;
+}
+
+void hb_shard_group_free(hb_shard_group* g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < g->n_shards; ++r)
+        if (g->opened[r]) cudaIpcCloseMemHandle(g->peer_base[r]);
+    cudaFree(g->d_peer_flags);
+    cudaFree(g->local);
+    delete g;
+}
+
+// Collective: every rank calls it with the same (nq, count, ef) and the same queries (all of them, device-resident).
+// Searches this rank's shard; the kernel's epilogue stores each query's padded top-k into every rank's gather buffer
+// over NVLink (no NCCL all-gather); a flag exchange orders it; the merge kernel then produces the global top-k in
+// d_out_* on every rank.  All on `stream`, no host synchronisation.
+hb_status hb_search_sharded_device(const hb_index* ix, hb_shard_group* g, const float* d_q, uint64_t nq, uint32_t count, uint32_t ef,
+                                   uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len, void* stream) {
+    if (!ix || !g || !d_q || !d_out_ids || !d_out_dist || !d_out_len) { set_error("null argument"); return HB_EINVAL; }
+    if (!ix->finalized) { set_error("index not finalized"); return HB_ESTATE; }
+    if (!g->d_peer_flags) { set_error("shard group not connected"); return HB_ESTATE; }
+    if (nq > g->nq_cap || count > g->k_cap || nq == 0 || count == 0) { set_error("batch exceeds the shard group's capacity"); return HB_EINVAL; }
+    if (ix->ids.empty()) { set_error("empty shard"); return HB_EINVAL; }
+    CUDA_TRY(cudaSetDevice(ix->device));
+    Workspace* w = nullptr;
+    hb_status st = acquire_ws(ix, &w, stream ? stream : (void*)1);
+    if (st != HB_OK) return st;
+    const uint32_t epoch = ++g->epoch;
+    const int par = epoch & 1;
+    SearchParams p;
+    p.q = d_q; p.nq = nq; p.count = count; p.ef_raw = ef; p.mode = 0;
+    p.out_ids = d_out_ids; p.out_dist = d_out_dist; p.out_len = d_out_len;   // this shard's own list also lands here (scratch)
+    p.n_peers = g->n_shards; p.shard_rank = g->rank;
+    for (int r = 0; r < g->n_shards; ++r) {
+        p.peer_ids[r] = (uint32_t*)((uint8_t*)g->peer_base[r] + g->off_ids[par]);
+        p.peer_dist[r] = (float*)((uint8_t*)g->peer_base[r] + g->off_dist[par]);
+    }
+    st = run_search(ix, w, p, stream);
+    cudaEventRecord((cudaEvent_t)w->busy, (cudaStream_t)stream);
+    w->last_stream = stream ? stream : (void*)1;
+    w->async_used = true;
+    release_ws(ix, w);
+    if (st != HB_OK) return st;
+    uint32_t* my_flags = (uint32_t*)((uint8_t*)g->local + g->off_flags);
+    if ((st = launch_peer_signal_wait(g->d_peer_flags, g->n_shards, g->rank, my_flags, epoch, stream)) != HB_OK) return st;
+    return launch_merge_topk((const uint32_t*)((uint8_t*)g->local + g->off_ids[par]), (const float*)((uint8_t*)g->local + g->off_dist[par]),
+                             (uint32_t)g->n_shards, nq, count, d_out_ids, d_out_dist, d_out_len, stream);
+}
+
 hb_status hb_exact_knn(const hb_index* ix, const float* q, uint64_t nq, uint32_t dims, uint32_t k, uint32_t* out_ids, float* out_dist) {
     if (!ix || (!q && nq) || !out_ids || !out_dist) { set_error("null argument"); return HB_EINVAL; }
     if (!ix->finalized) { set_error("index not finalized"); return HB_ESTATE; }

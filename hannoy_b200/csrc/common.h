@@ -54,6 +54,7 @@ struct DevIndex {
     const uint32_t* nbr0x = nullptr;
 };
 constexpr uint32_t FIXED_DEG = 32;
+constexpr int HB_MAX_SHARDS = 16;
 
 // One search call.
 struct SearchParams {
@@ -85,6 +86,11 @@ struct SearchParams {
     uint32_t q_smem_bytes = 0;         // per-warp query staging bytes
     uint32_t ring_slots = 0;           // KIND_F32_WARP: rows in flight per warp (multiple of ROW_GROUP), ring.cuh
     uint32_t ring_stride = 0;          // bytes between ring slots
+    // id-sharded search with the all-gather fused into the epilogue: every query's padded top-k is stored straight into
+    // each peer's gather buffer [shard][nq][count] over NVLink (peer_ids[p] / peer_dist[p] are peer-mapped device pointers)
+    uint32_t* peer_ids[HB_MAX_SHARDS] = {};
+    float* peer_dist[HB_MAX_SHARDS] = {};
+    int n_peers = 0, shard_rank = 0;
     int defer = 1;                     // layer 0, pass 0: overlap a chunk's heap update with the next pop's adjacency / visited traffic
 };
 #ifndef HB_ROW_GROUP
@@ -182,5 +188,6 @@ hb_status launch_merge_topk(const uint32_t* d_ids, const float* d_dist, uint32_t
                             uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len, void* stream);
 extern std::atomic<unsigned long long> g_launches;
 void read_phases(unsigned long long* out);
+hb_status launch_peer_signal_wait(uint32_t* const* peer_flags, int n_peers, int shard_rank, uint32_t* my_flags, uint32_t epoch, void* stream);
 uint32_t read_trace(unsigned long long* out, uint32_t cap);
 }  // namespace hb

@@ -777,6 +777,18 @@ __device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64*
         p.out_ids[qi * count + i] = __ldg(&ix.ids[(uint32_t)k]);
         p.out_dist[qi * count + i] = key_dist(k);
     }
+    if (p.n_peers) {
+        // fused all-gather: this shard's padded top-k of query qi goes straight into every peer's gather buffer
+        for (int pr = 0; pr < p.n_peers; ++pr) {
+            uint32_t* gi = p.peer_ids[pr] + ((size_t)p.shard_rank * p.nq + qi) * count;
+            float* gd = p.peer_dist[pr] + ((size_t)p.shard_rank * p.nq + qi) * count;
+            for (int i = lane; i < (int)count; i += 32) {
+                u64 k = i < n_out ? c.res[i] : 0;
+                gi[i] = i < n_out ? __ldg(&ix.ids[(uint32_t)k]) : 0xffffffffu;
+                gd[i] = i < n_out ? key_dist(k) : __int_as_float(0x7f800000);
+            }
+        }
+    }
     if (lane == 0) {
         p.out_len[qi] = (uint32_t)n_out;
         if (p.out_ctr) {
@@ -861,6 +873,38 @@ uint32_t read_trace(unsigned long long* out, uint32_t cap) {
     (void)out; (void)cap;
     return 0;
 #endif
+}
+
+// ---- peer synchronisation of the fused all-gather -----------------------------------------------------------
+// Runs behind the search kernel on the same stream: publish "shard `shard_rank` has delivered epoch `epoch`" in every
+// peer's flag array (system-scope release after the search kernel's peer stores), then wait until every shard has
+// published the same epoch here.  Bounded spin: a peer that never arrives makes the wait give up (flag 0xdead in
+// my_flags[n_peers]) instead of hanging the device.
+__global__ void peer_signal_wait_kernel(uint32_t* const* peer_flags, int n_peers, int shard_rank, uint32_t* my_flags, uint32_t epoch) {
+    const int t = threadIdx.x;
+    if (t < n_peers) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[t] + shard_rank), "r"(epoch) : "memory");
+    }
+    __syncthreads();
+    if (t < n_peers) {
+        uint32_t v = 0;
+        unsigned long long spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(my_flags + t) : "memory");
+            if ((int)(v - epoch) >= 0) break;
+            __nanosleep(200);
+        } while (++spins < 20000000ull);  // ~ 4 s
+        if ((int)(v - epoch) < 0) my_flags[n_peers] = 0xdead;
+    }
+}
+
+hb_status launch_peer_signal_wait(uint32_t* const* peer_flags, int n_peers, int shard_rank, uint32_t* my_flags, uint32_t epoch, void* stream) {
+    peer_signal_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(peer_flags, n_peers, shard_rank, my_flags, epoch);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("peer sync launch failed: %s", cudaGetErrorString(e)); return HB_ECUDA; }
+    return HB_OK;
 }
 
 __global__ void fill_iota_kernel(uint32_t* list, uint32_t* n_out, uint32_t n) {

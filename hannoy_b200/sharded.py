@@ -97,6 +97,49 @@ class ShardedSearcher:
                           o_dist.data_ptr(), o_len.data_ptr(), stream.cuda_stream)
         return o_ids, o_dist, o_len
 
+    # ---- all-gather fused into the search kernel (peer memory over NVLink, no NCCL in the data path) ----
+    def connect_fused(self, nq_cap, k_cap):
+        """Create this rank's exchange buffer, swap the CUDA-IPC handles (one small host-side all-gather, set-up only)
+        and map every peer's buffer.  Afterwards `search_device_fused` needs no collective library call."""
+        import ctypes as C
+        import torch
+        from . import _lib as L
+        from .reader import _check
+        dev = self.device if self.device is not None else torch.cuda.current_device()
+        g = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        _check(L.lib().hb_shard_group_create(dev, self.world, self.rank, nq_cap, k_cap, C.byref(g), C.cast(handle, C.c_void_p)))
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=torch.device("cuda", dev) if self.dist.get_backend(self.group) == "nccl" else "cpu")
+        allh = torch.empty((self.world, 64), dtype=torch.uint8, device=mine.device)
+        self.dist.all_gather_into_tensor(allh, mine, group=self.group)
+        raw = bytes(allh.cpu().numpy().tobytes())
+        _check(L.lib().hb_shard_group_connect(g, raw))
+        self._group_handle = g
+        self.dist.barrier(group=self.group)
+        return self
+
+    def search_device_fused(self, d_q, count, ef):
+        """Collective.  Like search_device, but the per-shard top-k lists travel inside the search kernel's epilogue
+        (stores into every peer's gather buffer) instead of through an all-gather."""
+        import torch
+        from . import _lib as L
+        from .reader import _check
+        nq = d_q.shape[0]
+        dev = d_q.device
+        stream = torch.cuda.current_stream(dev)
+        o_ids = torch.empty((nq, count), dtype=torch.int32, device=dev)
+        o_dist = torch.empty((nq, count), dtype=torch.float32, device=dev)
+        o_len = torch.empty((nq,), dtype=torch.int32, device=dev)
+        _check(L.lib().hb_search_sharded_device(self.reader._h, self._group_handle, d_q.data_ptr(), nq, count, max(ef, count),
+                                                o_ids.data_ptr(), o_dist.data_ptr(), o_len.data_ptr(), stream.cuda_stream))
+        return o_ids, o_dist, o_len
+
+    def close_fused(self):
+        from . import _lib as L
+        if getattr(self, "_group_handle", None):
+            L.lib().hb_shard_group_free(self._group_handle)
+            self._group_handle = None
+
     def search(self, q, count, ef):
         import torch
         if self.reader is not None and self.dist.get_backend(self.group) == "nccl" and self.local_search == self._cuda_local_search:

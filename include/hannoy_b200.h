@@ -140,6 +140,21 @@ hb_status hb_exact_knn(const hb_index*, const float* q, uint64_t nq, uint32_t di
 hb_status hb_merge_topk_device(int device, const uint32_t* d_ids, const float* d_dist, uint32_t n_parts, uint64_t nq,
                                uint32_t k, uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len, void* stream);
 
+/* ---- id-sharded index with the all-gather fused into the search kernel (no reference counterpart: hannoy is
+ * single-node; shard s = hannoy index s, src/key.rs:19-23) -------------------------------------------------------
+ * One process per GPU.  Each rank creates its exchange buffer and gets a 64-byte CUDA-IPC handle; the ranks exchange
+ * the handles (any host all-gather) and connect.  hb_search_sharded_device is then a collective: every rank passes
+ * ALL queries (device-resident); the search kernel's epilogue stores each query's padded per-shard top-k straight into
+ * every peer's gather buffer over NVLink, a flag exchange orders it, and the merge kernel leaves the global top-k by
+ * (distance bits, id) in d_out_* on every rank.  Capacity: nq <= nq_cap, count <= k_cap, n_shards <= 16. */
+typedef struct hb_shard_group hb_shard_group;
+hb_status hb_shard_group_create(int device, int n_shards, int rank, uint64_t nq_cap, uint32_t k_cap, hb_shard_group** out,
+                                uint8_t handle_out[64]);
+hb_status hb_shard_group_connect(hb_shard_group*, const uint8_t* handles /* n_shards x 64 bytes, rank order */);
+hb_status hb_search_sharded_device(const hb_index*, hb_shard_group*, const float* d_q, uint64_t nq, uint32_t count, uint32_t ef,
+                                   uint32_t* d_out_ids, float* d_out_dist, uint32_t* d_out_len, void* stream);
+void hb_shard_group_free(hb_shard_group*);
+
 /* number of kernel launches issued by this library in this process (for bench gpu_launches) */
 uint64_t hb_launch_count(void);
 

@@ -78,6 +78,19 @@ def _worker_body(rank, world, port, ret):
         ok &= [int(v) for v in got[1][i, :len(keys)].view(np.uint32)] == [kk[0] for kk in keys]
         if not ok and len(why) < 3:
             why.append(f"shard merge query {i}: got {got[0][i].tolist()} len {int(got[2][i])}, want {[kk[1] for kk in keys]}")
+    # ---- the same search with the all-gather fused into the kernel epilogue (peer memory, no NCCL in the data path) ----
+    ss = ShardedSearcher(reader=rs, device=rank).connect_fused(nq_cap=len(q), k_cap=k)
+    d_q = torch.from_numpy(q).to(torch.device("cuda", rank))
+    for rep in range(3):   # several epochs: exercises the double-buffered exchange
+        f_ids, f_dist, f_len = ss.search_device_fused(d_q, k, ef)
+    torch.cuda.synchronize()
+    same = (np.array_equal(f_ids.cpu().numpy().view(np.uint32), got[0]) and np.array_equal(f_dist.cpu().numpy().view(np.uint32), got[1].view(np.uint32))
+            and np.array_equal(f_len.cpu().numpy().view(np.uint32), got[2]))
+    if not same:
+        ok = False
+        why.append("fused peer-memory exchange differs from the NCCL all-gather path")
+    dist.barrier()
+    ss.close_fused()
     ret[rank] = True if ok else "; ".join(why)
     dist.barrier()
     dist.destroy_process_group()
