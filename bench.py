@@ -36,6 +36,10 @@ WORKLOADS = {
                desc="1M x 768 f32 Cosine (text-embedding shaped), 10k-query batch, top-10"),
     "c4s": dict(metric="binary quantized cosine", n=1_000_000, dims=1024, nq=100_000, k=100, efs=[100, 200, 400], gen="lowrank", seed=7,
                 desc="1M x 1024 BinaryQuantizedCosine codes (scaled-down config 4), 100k-query batch, top-100"),
+    # config 5, scaled: index sharded by item id (id % n_gpus), every GPU searches ALL queries on its shard, per-shard
+    # top-k exchanged over NVLink and merged.  n = items PER SHARD.
+    "c5s": dict(metric="cosine", n=250_000, dims=768, nq=20_000, k=10, efs=[128], gen="lowrank", seed=9, sharded=True,
+                desc="id-sharded 768-d f32 Cosine, 250k items per shard/GPU, 20k-query batch searched by every shard, top-10, top-k exchange + merge"),
 }
 M, M0, EFC, ALPHA = 16, 32, 100, 1.0
 RECALL_TARGET = 0.95
@@ -246,6 +250,9 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
+    if w.get("sharded"):
+        return run_sharded(args, w, rank, world, local_rank, dev, use_dist, threads, log)
+
     # ---- synthetic data (seeded) ----
     t0 = time.time()
     x = gen_vectors(w["gen"], w["n"], w["dims"], w["seed"], dev)
@@ -436,6 +443,86 @@ def main():
     if use_dist:
         dist.barrier()
         dist.destroy_process_group()
+    return 0
+
+
+def run_sharded(args, w, rank, world, local_rank, dev, use_dist, threads, log):
+    """Config-5-shaped run: shard `rank` holds the items with id % world == rank (its own graph = one hannoy index per
+    shard, src/key.rs:19-23).  A step = every rank searches the whole query batch on its shard, the per-shard top-k
+    lists are exchanged and merged on every rank.  Two exchanges are timed: NCCL all-gather, and the exchange fused
+    into the search kernel's epilogue (peer-memory stores over NVLink).  value = queries / step time."""
+    import torch
+    import torch.distributed as dist
+    import hannoy_b200 as hb
+    from hannoy_b200.sharded import ShardedSearcher
+    from oracle.oracle import OracleDb
+    if not use_dist:
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the sharded workload has no single-process CPU arm; use the default workload"}))
+            return 0
+        dist.init_process_group("nccl" if dev.type == "cuda" else "gloo", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1,
+                                **({"device_id": dev} if dev.type == "cuda" else {}))
+    n, dims, nq, k, ef = w["n"], w["dims"], w["nq"], w["k"], w["efs"][0]
+    x = gen_vectors(w["gen"], n, dims, w["seed"] + 100 * rank, dev).cpu().numpy()
+    q = gen_vectors(w["gen"], nq, dims, w["seed"] + 1, dev)
+    q_host = q.cpu().numpy()
+    ids = (np.arange(n, dtype=np.uint64) * world + rank).astype(np.uint32)
+    db = OracleDb(w["metric"], dims)
+    db.add_items(ids, x)
+    t0 = time.time()
+    db.build(M=M, M0=M0, ef_construction=EFC, alpha=ALPHA, seed=42 + rank, n_threads=max(1, threads // world))
+    log(f"shard {rank}: graph of {n} items built in {time.time() - t0:.1f}s")
+    rd = hb.Reader.from_arrays(w["metric"], dims, db.ids(), db.rows(), db.headers(), db.layers(), db.entry_points, db.max_level,
+                               index=rank, device=local_rank)
+    ss = ShardedSearcher(reader=rd, device=local_rank).connect_fused(nq_cap=nq, k_cap=k)
+    stream = torch.cuda.current_stream()
+
+    def timed(fn):
+        for _ in range(max(args.warmup, 3)):
+            out = fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            out = fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), out
+
+    from hannoy_b200 import _lib
+    ms_nccl, out_nccl = timed(lambda: ss.search_device(q, k, ef))
+    l0 = _lib.lib().hb_launch_count()
+    ms_fused, out_fused = timed(lambda: ss.search_device_fused(q, k, ef))
+    launches = (_lib.lib().hb_launch_count() - l0) * args.steps // (args.steps + max(args.warmup, 3))
+    same = all(bool(torch.equal(a, b)) for a, b in zip(out_nccl, out_fused))
+    # parity: the reference reader on each shard index, merged by (distance bits, id), on a sample of the batch
+    n_par = 64
+    mine = db.search_by_vector(q_host[:n_par], k, ef=max(ef, k), n_threads=max(1, threads // world))
+    parts = [None] * world
+    dist.all_gather_object(parts, (mine[0], mine[1], mine[2]))
+    parity_ok = True
+    gi, gd = out_fused[0][:n_par].cpu().numpy().view(np.uint32), out_fused[1][:n_par].cpu().numpy().view(np.uint32)
+    for i in range(n_par):
+        keys = sorted((int(p[1][i, j:j + 1].view(np.uint32)[0]), int(p[0][i, j])) for p in parts for j in range(int(p[2][i])))[:k]
+        parity_ok &= gi[i, :len(keys)].tolist() == [kk[1] for kk in keys] and gd[i, :len(keys)].tolist() == [kk[0] for kk in keys]
+    if rank == 0:
+        line = {"metric": "QPS (batched, id-sharded index)", "value": round(nq / (ms_fused / 1e3), 1), "unit": "queries/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_fused, 4), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": w["desc"], "metric": w["metric"], "items_per_shard": n, "n_shards": world, "dims": dims, "batch_queries": nq,
+                           "k": k, "ef_search": ef, "exchange": "fused into the search kernel epilogue (peer-memory stores over NVLink) + merge kernel",
+                           "nccl_all_gather_ms_per_step": round(ms_nccl, 4), "nccl_all_gather_qps": round(nq / (ms_nccl / 1e3), 1),
+                           "fused_equals_nccl": same, "parity_vs_oracle": "bit-exact" if parity_ok else "MISMATCH",
+                           "cache": "inputs larger than L2"},
+                "gpu_launches": int(launches)}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    ss.close_fused()
+    dist.destroy_process_group()
     return 0
 
 
