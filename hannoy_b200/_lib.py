@@ -18,7 +18,8 @@ FLAG_FALLBACK, FLAG_LINEAR, FLAG_SLOW_PATH = 1, 2, 4
 
 # every symbol include/hannoy_b200.h declares
 EXPORTS = [
-    "hb_metric_name", "hb_metric_from_name", "hb_index_begin", "hb_index_push_kv", "hb_index_from_arrays",
+    "hb_metric_name", "hb_metric_from_name", "hb_index_begin", "hb_index_push_kv", "hb_index_push_lmdb", "hb_index_open_lmdb",
+    "hb_lmdb_scan", "hb_index_from_arrays",
     "hb_index_finalize", "hb_index_free", "hb_index_dimensions", "hb_index_n_items", "hb_index_n_entry_points",
     "hb_index_max_level", "hb_index_version", "hb_index_item_ids", "hb_index_contains_item", "hb_index_item_vector",
     "hb_search_by_vector", "hb_search_by_item", "hb_search_by_vector_device", "hb_exact_knn", "hb_merge_topk_device",
@@ -31,6 +32,8 @@ class QueryOpts(C.Structure):
     _fields_ = [("candidates", C.c_void_p), ("n_candidates", C.c_uint64), ("has_candidates", C.c_int),
                 ("linear_below", C.c_uint32), ("linear_below_ratio", C.c_float)]
 
+
+KV_VISIT = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_ubyte), C.c_size_t, C.POINTER(C.c_ubyte), C.c_size_t)
 
 _lib = None
 
@@ -50,6 +53,9 @@ def lib():
         "hb_metric_name": (C.c_char_p, [i32]), "hb_metric_from_name": (i32, [C.c_char_p]),
         "hb_index_begin": (i32, [i32, u16, C.POINTER(vp)]),
         "hb_index_push_kv": (i32, [vp, C.c_char_p, sz, C.c_char_p, sz]),
+        "hb_index_push_lmdb": (i32, [vp, C.c_char_p, C.c_char_p, C.POINTER(u64)]),
+        "hb_index_open_lmdb": (i32, [C.c_char_p, C.c_char_p, i32, u16, i32, C.POINTER(vp)]),
+        "hb_lmdb_scan": (i32, [C.c_char_p, C.c_char_p, C.c_char_p, sz, KV_VISIT, vp, C.POINTER(u64)]),
         "hb_index_from_arrays": (i32, [vp, u32, vp, u64, vp, vp, u32, vp, vp, vp, u32, u32]),
         "hb_index_finalize": (i32, [vp, i32]), "hb_index_free": (None, [vp]),
         "hb_index_dimensions": (u32, [vp]), "hb_index_n_items": (u64, [vp]),

@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["capi.cu", "search.cu", "exact.cu", "snapshot.cpp"]
+SOURCES = ["capi.cu", "search.cu", "exact.cu", "snapshot.cpp", "lmdb_walk.cpp"]
 HEADERS = ["common.h", "dist.cuh", "sorted.cuh", "ring.cuh", os.path.join("..", "..", "include", "hannoy_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

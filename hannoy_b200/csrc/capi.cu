@@ -112,6 +112,61 @@ hb_status hb_index_push_kv(hb_index* ix, const uint8_t* key, size_t klen, const 
     }
 }
 
+// ---- LMDB route: the environment on disk is read directly (lmdb_walk.cpp) ---------------------------------------
+struct PushCtx { hb_index* ix; uint64_t n; };
+static hb_status push_cb(void* u, const uint8_t* k, size_t kl, const uint8_t* v, size_t vl, unsigned) {
+    PushCtx* c = (PushCtx*)u;
+    ++c->n;
+    return decode_kv(c->ix, k, kl, v, vl);
+}
+struct UserCtx { hb_kv_visit fn; void* user; };
+static hb_status user_cb(void* u, const uint8_t* k, size_t kl, const uint8_t* v, size_t vl, unsigned) {
+    UserCtx* c = (UserCtx*)u;
+    if (c->fn(c->user, k, kl, v, vl) != 0) { set_error("hb_lmdb_scan: stopped by the visitor"); return HB_ESTATE; }
+    return HB_OK;
+}
+
+hb_status hb_lmdb_scan(const char* path, const char* db_name, const uint8_t* prefix, size_t prefix_len, hb_kv_visit fn, void* user,
+                       uint64_t* txnid_out) {
+    if (!path || !fn || (!prefix && prefix_len)) { set_error("hb_lmdb_scan: null argument"); return HB_EINVAL; }
+    try {
+        UserCtx c{fn, user};
+        return lmdb_scan(path, db_name, prefix, prefix_len, user_cb, &c, txnid_out);
+    } catch (const std::bad_alloc&) {
+        return HB_ENOMEM;
+    }
+}
+
+hb_status hb_index_push_lmdb(hb_index* ix, const char* path, const char* db_name, uint64_t* n_pairs_out) {
+    if (!ix || !path) { set_error("hb_index_push_lmdb: null argument"); return HB_EINVAL; }
+    if (ix->finalized) { set_error("index already finalized"); return HB_ESTATE; }
+    try {
+        const uint8_t prefix[2] = {(uint8_t)(ix->index >> 8), (uint8_t)(ix->index & 0xff)};  // KeyCodec: index is big-endian, src/key.rs:57-60
+        PushCtx c{ix, 0};
+        hb_status st = lmdb_scan(path, db_name, prefix, 2, push_cb, &c, nullptr);
+        if (n_pairs_out) *n_pairs_out = c.n;
+        return st;
+    } catch (const std::bad_alloc&) {
+        return HB_ENOMEM;
+    }
+}
+
+hb_status hb_index_open_lmdb(const char* path, const char* db_name, hb_metric m, uint16_t index, int device, hb_index** out) {
+    if (!out) { set_error("hb_index_open_lmdb: null argument"); return HB_EINVAL; }
+    *out = nullptr;
+    hb_status st = HB_OK;
+    for (int attempt = 0; attempt < 4; ++attempt) {  // HB_ESTATE = a writer committed under the walk: take a fresh snapshot
+        hb_index* ix = nullptr;
+        if ((st = hb_index_begin(m, index, &ix)) != HB_OK) return st;
+        st = hb_index_push_lmdb(ix, path, db_name, nullptr);
+        if (st == HB_OK) st = hb_index_finalize(ix, device);
+        if (st == HB_OK) { *out = ix; return HB_OK; }
+        hb_index_free(ix);
+        if (st != HB_ESTATE) break;
+    }
+    return st;
+}
+
 hb_status hb_index_from_arrays(hb_index* ix, uint32_t dims, const uint32_t* ids, uint64_t n, const void* rows,
                                const float* hdr, uint32_t n_layers, const uint64_t* const* offsets,
                                const uint32_t* const* nbrs, const uint32_t* entry_points, uint32_t n_ep,

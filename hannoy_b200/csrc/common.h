@@ -144,7 +144,9 @@ struct hb_index {
     uint32_t meta_max_level = 0;
     uint32_t version[3] = {0, 0, 0};
     bool need_build = false;
-    std::map<uint32_t, std::vector<uint8_t>> kv_items;                    // id -> header||vector bytes
+    std::map<uint32_t, std::vector<uint8_t>> kv_items;                    // id -> header||vector bytes (pairs seen before the metadata)
+    bool direct_rows = false;        // metadata seen first (always, in LMDB key order): items go straight into host_rows
+    std::vector<uint8_t> row_seen;   // per slot
     std::map<std::pair<uint32_t, uint32_t>, std::vector<uint32_t>> kv_links;  // (id, layer) -> ids
     // --- canonical host snapshot ---
     uint32_t dims = 0;
@@ -170,6 +172,10 @@ hb_status decode_kv(hb_index* ix, const uint8_t* key, size_t klen, const uint8_t
 hb_status build_host_snapshot_from_kv(hb_index* ix);
 bool roaring_decode(const uint8_t* p, size_t len, std::vector<uint32_t>& out);
 int64_t slot_of(const hb_index* ix, uint32_t id);
+// lmdb_walk.cpp: in-order walk of one database of an LMDB data file, restricted to keys starting with `prefix`
+typedef hb_status (*lmdb_visit_fn)(void* user, const uint8_t* key, size_t klen, const uint8_t* val, size_t vlen, unsigned node_flags);
+hb_status lmdb_scan(const char* path, const char* db_name, const uint8_t* prefix, size_t prefix_len, lmdb_visit_fn fn, void* user,
+                    uint64_t* txnid_out);
 // device row layout
 uint32_t device_row_stride(int kind, uint32_t dims);
 void layout_row(int kind, uint32_t dims, const uint8_t* natural, uint8_t* out);

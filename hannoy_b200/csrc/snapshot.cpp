@@ -88,6 +88,7 @@ bool roaring_decode(const uint8_t* p, size_t len, std::vector<uint32_t>& out) {
 }
 
 static size_t header_size(hb_metric m) { return m == HB_HAMMING ? 8 : 4; }  // NodeHeaderHamming{idx: usize}
+static size_t natural_row_bytes(hb_metric m, uint32_t dims) { return m >= HB_HAMMING ? 8 * (((size_t)dims + 63) / 64) : 4 * (size_t)dims; }
 
 // One raw LMDB pair.  Key = [index u16 BE][mode u8][item u32 BE][layer u8] (src/key.rs:54-82);
 // modes Metadata=0 Updated=1 Links=2 Item=3 (src/node_id.rs:11-21).
@@ -101,6 +102,7 @@ hb_status decode_kv(hb_index* ix, const uint8_t* key, size_t klen, const uint8_t
     switch (mode) {
         case 0: {
             if (item == 0) {  // MetadataCodec — src/metadata.rs:49-73
+                if (ix->direct_rows) { set_error("metadata pushed again after items were decoded against it"); return HB_ESTATE; }
                 const void* nul = std::memchr(val, 0, vlen);
                 if (!nul) { set_error("metadata: distance name not NUL-terminated"); return HB_EFORMAT; }
                 size_t nl = (const uint8_t*)nul - val;
@@ -140,11 +142,31 @@ hb_status decode_kv(hb_index* ix, const uint8_t* key, size_t klen, const uint8_t
             return HB_OK;
         }
         case 3: {  // Item — src/node.rs:154-160: [0][header][vector bytes]
+            // Reader::open compares the stored distance name before any item is decoded (reader.rs:400-405): with the
+            // metadata already seen (always, in key order) and another distance stored, finalize reports UnmatchingDistance
+            if (ix->have_metadata && ix->meta_distance != hb_metric_name(ix->metric)) return HB_OK;
             size_t hs = header_size(ix->metric);
             if (vlen < 1 + hs || val[0] != 0) { set_error("item node: bad tag or truncated"); return HB_EFORMAT; }
             size_t vb = vlen - 1 - hs;
             size_t unit = ix->metric >= HB_HAMMING ? 8 : 4;
             if (vb % unit) { set_error("item node: %zu trailing bytes", vb % unit); return HB_EFORMAT; }  // SizeMismatch
+            if (ix->have_metadata) {  // the usual order: no staging copy, the row lands in its slot
+                const std::vector<uint32_t>& mi = ix->meta_items;
+                auto it = std::lower_bound(mi.begin(), mi.end(), item);
+                if (it == mi.end() || *it != item) return HB_OK;  // not listed in the metadata: never read by the Reader
+                size_t s = (size_t)(it - mi.begin()), rb = natural_row_bytes(ix->metric, ix->meta_dims);
+                if (!ix->direct_rows) {
+                    ix->host_rows.assign(mi.size() * rb, 0);
+                    ix->host_hdr.assign(mi.size(), 0.0f);
+                    ix->row_seen.assign(mi.size(), 0);
+                    ix->direct_rows = true;
+                }
+                if (vb < rb) { set_error("item %u: vector shorter than the index dimensions", item); return HB_EFORMAT; }
+                if (hs == 4) std::memcpy(&ix->host_hdr[s], val + 1, 4);
+                std::memcpy(ix->host_rows.data() + s * rb, val + 1 + hs, rb);
+                ix->row_seen[s] = 1;
+                return HB_OK;
+            }
             ix->kv_items[item].assign(val + 1, val + vlen);
             return HB_OK;
         }
@@ -170,12 +192,14 @@ hb_status build_host_snapshot_from_kv(hb_index* ix) {
     ix->dims = ix->meta_dims;
     ix->ids = ix->meta_items;  // already ascending
     size_t n = ix->ids.size();
-    bool bin = ix->metric >= HB_HAMMING;
-    ix->host_row_bytes = bin ? 8 * (((size_t)ix->dims + 63) / 64) : 4 * (size_t)ix->dims;
+    ix->host_row_bytes = natural_row_bytes(ix->metric, ix->dims);
     size_t hs = header_size(ix->metric);
-    ix->host_rows.assign(n * ix->host_row_bytes, 0);
-    ix->host_hdr.assign(n, 0.0f);
+    if (!ix->direct_rows) {
+        ix->host_rows.assign(n * ix->host_row_bytes, 0);
+        ix->host_hdr.assign(n, 0.0f);
+    }
     for (size_t s = 0; s < n; ++s) {
+        if (ix->direct_rows && ix->row_seen[s]) continue;
         auto it = ix->kv_items.find(ix->ids[s]);
         if (it == ix->kv_items.end()) { set_error("item %u listed in metadata has no Item node", ix->ids[s]); return HB_EFORMAT; }
         const std::vector<uint8_t>& v = it->second;
@@ -216,6 +240,7 @@ hb_status build_host_snapshot_from_kv(hb_index* ix) {
     ix->max_level = ix->meta_max_level;
     ix->kv_items.clear();
     ix->kv_links.clear();
+    std::vector<uint8_t>().swap(ix->row_seen);
     return HB_OK;
 }
 

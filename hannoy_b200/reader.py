@@ -9,6 +9,7 @@ Differences from the Rust API, all forced by the snapshot design:
   * cancellation closures cannot cross the ABI: `did_cancel` is always False.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -259,6 +260,17 @@ class Reader:
         except Exception:
             lib.hb_index_free(h)
             raise
+        return cls(h, d, index)
+
+    @classmethod
+    def open_path(cls, path, index, distance, db_name=None, device=0):
+        """Reader::open from an LMDB environment on disk (directory holding data.mdb, or the data file): the library
+        walks the B+tree itself (hb_index_open_lmdb) — the `(&RoTxn, index, Database<D>)` triple of reader.rs:387
+        becomes `(path, db_name)`; `db_name=None` is the unnamed database."""
+        d = _distance_of(distance)
+        h = C.c_void_p()
+        _check(L.lib().hb_index_open_lmdb(os.fsencode(path), db_name.encode() if db_name else None, d.ID, index, device,
+                                          C.byref(h)))
         return cls(h, d, index)
 
     @classmethod

@@ -66,6 +66,24 @@ hb_status hb_index_begin(hb_metric m, uint16_t index, hb_index** out);
  * Updated stones (src/update_status.rs) and the Roaring portable format (src/roaring.rs:14-32). */
 hb_status hb_index_push_kv(hb_index*, const uint8_t* key, size_t klen, const uint8_t* val, size_t vlen);
 
+/* Route (a'): read the LMDB environment on disk directly — what `Reader::open(&rtxn, index, database)` does through
+ * heed (src/reader.rs:387-431; environment opened as in src/tests/mod.rs:108-111, benches/speed.rs:39-53), without
+ * liblmdb or Rust.  `path` = the environment directory (holding data.mdb) or the data file itself (MDB_NOSUBDIR);
+ * `db_name` = NULL/"" for the unnamed database (`env.create_database(&mut wtxn, None)`) or the name of a named one.
+ * The B+tree is walked once in key order restricted to the index's 2-byte big-endian key prefix (src/key.rs:57-60,
+ * the range `Prefix::all(index)` iterates, src/key.rs:94-127); every pair goes through the same decoder as
+ * hb_index_push_kv.  The newest committed transaction is read; if a writer commits while the file is being walked the
+ * call returns HB_ESTATE (hb_index_open_lmdb retries with a fresh snapshot).  n_pairs_out (optional) = pairs read. */
+hb_status hb_index_push_lmdb(hb_index*, const char* path, const char* db_name, uint64_t* n_pairs_out);
+/* hb_index_begin + hb_index_push_lmdb + hb_index_finalize: Reader::open from a path. */
+hb_status hb_index_open_lmdb(const char* path, const char* db_name, hb_metric m, uint16_t index, int device, hb_index** out);
+/* The walker on its own: visits every (key, value) of the database whose key starts with `prefix` (prefix_len may be
+ * 0), in key order; the pointers are only valid during the callback; a non-zero return stops the scan (HB_ESTATE).
+ * txnid_out (optional) = id of the LMDB transaction that was read. */
+typedef int (*hb_kv_visit)(void* user, const uint8_t* key, size_t klen, const uint8_t* val, size_t vlen);
+hb_status hb_lmdb_scan(const char* path, const char* db_name, const uint8_t* prefix, size_t prefix_len, hb_kv_visit fn,
+                       void* user, uint64_t* txnid_out);
+
 /* Route (b): flat arrays (bench / tests).  ids ascending & unique; rows = n x dims f32 (float
  * metrics) or n x ceil(dims/64) u64 code words (binary metrics); hdr = n header norms (Cosine,
  * BQ-Cosine) or NULL; per layer l: offsets[l] has n+1 u64 entries, nbrs[l] holds neighbour ITEM IDS,

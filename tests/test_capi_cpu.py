@@ -132,6 +132,29 @@ def test_kv_decode_matches_what_was_written(metric):
     lib.hb_index_free(h)
 
 
+@pytest.mark.parametrize("order", ["sorted", "reversed", "shuffled"])
+def test_push_kv_accepts_any_order(order):
+    """Sorted (LMDB cursor) order sees the metadata first and writes rows straight into their slots; any other order
+    is staged and resolved at finalize.  Same snapshot either way."""
+    n, dims = 200, 33
+    db, x = make_db("cosine", n, dims, seed=5)
+    kv = sorted((bytes(k), bytes(v)) for k, v in db.export_kv(1))
+    if order == "reversed":
+        kv = kv[::-1]
+    elif order == "shuffled":
+        kv = [kv[i] for i in np.random.default_rng(0).permutation(len(kv))]
+    lib = L.lib()
+    h = _begin(1, index=1)
+    _push_all(h, kv)
+    assert lib.hb_index_finalize(h, 0) in (L.HB_OK, L.HB_ECUDA)
+    assert lib.hb_index_n_items(h) == n
+    v = np.zeros(dims, np.float32)
+    for s in range(0, n, 7):
+        assert lib.hb_index_item_vector(h, s, v.ctypes.data_as(C.c_void_p)) == L.HB_OK
+        assert np.array_equal(v, x[s])
+    lib.hb_index_free(h)
+
+
 def test_python_mirror_surface():
     """The host mirror keeps the reference names: Reader.open/nns, QueryBuilder.ef_search/candidates/linear_below(_ratio)/
     by_vector/by_item, Searched.into_nns/did_cancel, and the defaults of reader.rs:23-32."""

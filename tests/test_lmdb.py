@@ -1,0 +1,233 @@
+"""Native LMDB ingestion: Reader::open straight from a data.mdb, walked by the product's own read-only
+B+tree walker (hannoy_b200/csrc/lmdb_walk.cpp) — no liblmdb, no heed.  The files are produced by tests/lmdb_writer.py
+(liblmdb is absent from this image; see its header for what that means for format pinning)."""
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from helpers import assert_same, make_db, make_vectors
+from lmdb_writer import LmdbWriter
+from hannoy_b200 import _lib as L
+import hannoy_b200 as hb
+
+
+def _scan(path, db_name=None, prefix=b""):
+    got = []
+
+    def cb(user, k, kl, v, vl):
+        got.append((bytes(k[:kl]), bytes(v[:vl])))
+        return 0
+
+    txn = C.c_uint64()
+    st = L.lib().hb_lmdb_scan(os.fsencode(path), db_name.encode() if db_name else None, prefix, len(prefix), L.KV_VISIT(cb), None,
+                              C.byref(txn))
+    return st, got, txn.value
+
+
+def _random_pairs(n, seed, big_every=0, klen=8):
+    rng = np.random.default_rng(seed)
+    keys = sorted({bytes(rng.integers(0, 256, klen, dtype=np.uint8)) for _ in range(n)})
+    pairs = []
+    for i, k in enumerate(keys):
+        ln = int(rng.integers(0, 300))
+        if big_every and i % big_every == 0:
+            ln = int(rng.integers(2000, 20000))  # forces overflow pages
+        pairs.append((k, bytes(rng.integers(0, 256, ln, dtype=np.uint8))))
+    return pairs
+
+
+@pytest.mark.parametrize("n,psize,fill,big_every", [(0, 4096, 1.0, 0), (1, 4096, 1.0, 0), (40, 4096, 1.0, 0), (3000, 4096, 1.0, 7),
+                                                    (3000, 4096, 0.55, 0), (20000, 4096, 0.7, 50), (2500, 16384, 0.8, 5),
+                                                    (1500, 512, 1.0, 9)])
+def test_scan_returns_every_pair_in_key_order(tmp_path, n, psize, fill, big_every):
+    pairs = _random_pairs(n, seed=n + psize, big_every=big_every)
+    w = LmdbWriter(psize=psize, fill=fill)
+    w.put_unnamed(pairs)
+    w.save(str(tmp_path / "env"), txnid=11)
+    st, got, txn = _scan(str(tmp_path / "env"))
+    assert st == L.HB_OK, L.lib().hb_last_error()
+    assert txn == 11
+    assert got == pairs
+
+
+def test_scan_prefix_range_named_databases_meta_choice_and_nosubdir(tmp_path):
+    pairs = _random_pairs(6000, seed=5, big_every=11)
+    w = LmdbWriter(fill=0.8, junk_branch_key0=True)  # a reader must never look at a branch page's first key
+    w.put_named("vectors", pairs)
+    other = _random_pairs(300, seed=6)
+    w.put_named("documents", other)
+    w.put_named("vectors-old", [])
+    fn = w.save(str(tmp_path / "env.mdb"), txnid=3, newest_meta=0, nosubdir=True)  # meta page 0 is the newer one
+    for prefix in (b"", pairs[0][0][:1], pairs[3000][0][:2], pairs[-1][0][:2], b"\x00", b"\xff\xff"):
+        st, got, txn = _scan(fn, "vectors", prefix)
+        assert st == L.HB_OK, L.lib().hb_last_error()
+        assert txn == 3
+        assert got == [p for p in pairs if p[0].startswith(prefix)]
+    st, got, _ = _scan(fn, "documents")
+    assert st == L.HB_OK and got == other
+    st, got, _ = _scan(fn, "vectors-old")
+    assert st == L.HB_OK and got == []
+    st, got, _ = _scan(fn, "nope")
+    assert st == L.HB_EINVAL and b"no database named" in L.lib().hb_last_error()
+    # the unnamed database of this environment holds the three sub-database records
+    st, got, _ = _scan(fn)
+    assert st == L.HB_OK and [k for k, _ in got] == [b"documents", b"vectors", b"vectors-old"]
+
+
+def test_stale_meta_page_is_not_read(tmp_path):
+    """The meta page with the smaller txnid describes the previous commit; only the newest is used."""
+    old = _random_pairs(50, seed=1)
+    new = _random_pairs(80, seed=2)
+    w = LmdbWriter()
+    stale = w.build_tree(old)
+    w.put_unnamed(new)
+    for newest in (0, 1):
+        w.save(str(tmp_path / f"e{newest}"), txnid=100, newest_meta=newest, stale_main=stale)
+        st, got, txn = _scan(str(tmp_path / f"e{newest}"))
+        assert st == L.HB_OK and txn == 100 and got == new
+
+
+def test_corrupt_files_are_rejected_not_crashed_on(tmp_path):
+    pairs = _random_pairs(4000, seed=9, big_every=13)
+    w = LmdbWriter()
+    w.put_unnamed(pairs)
+    fn = w.save(str(tmp_path / "env"))
+    blob = bytearray(open(fn, "rb").read())
+    lib = L.lib()
+
+    def run(mut):
+        b = bytearray(blob)
+        mut(b)
+        p = str(tmp_path / "bad.mdb")
+        open(p, "wb").write(b)
+        return _scan(p)[0]
+
+    assert run(lambda b: b.__setitem__(slice(16, 20), b"\0\0\0\0")) == L.HB_EFORMAT            # magic of meta 0
+    assert b"not an LMDB data file" in lib.hb_last_error()
+    assert run(lambda b: b.__delitem__(slice(len(b) // 2, len(b)))) == L.HB_EFORMAT            # truncated file
+    root = w.main.root
+
+    def self_loop(b):  # first child of the root points back at the root
+        off = root * 4096
+        ptr0 = struct.unpack_from("<H", b, off + 16)[0]
+        struct.pack_into("<HHH", b, off + ptr0, root & 0xffff, (root >> 16) & 0xffff, 0)
+    assert run(self_loop) == L.HB_EFORMAT
+
+    def wild_ptr(b):
+        struct.pack_into("<H", b, root * 4096 + 16, 4095)
+    assert run(wild_ptr) == L.HB_EFORMAT
+
+    def bad_flags(b):
+        struct.pack_into("<H", b, root * 4096 + 10, 0)
+    assert run(bad_flags) == L.HB_EFORMAT
+    assert _scan(str(tmp_path / "missing"))[0] == L.HB_EINVAL
+    open(str(tmp_path / "tiny"), "wb").write(b"abc")
+    assert _scan(str(tmp_path / "tiny"))[0] == L.HB_EFORMAT
+
+
+def test_commit_during_the_walk_is_detected(tmp_path):
+    """No reader-table slot is taken, so a commit landing while the file is walked invalidates the snapshot: the scan
+    reports HB_ESTATE instead of returning possibly recycled pages."""
+    pairs = _random_pairs(500, seed=3)
+    w = LmdbWriter()
+    w.put_unnamed(pairs)
+    fn = w.save(str(tmp_path / "env"), txnid=20, newest_meta=1)
+    seen = []
+
+    def cb(user, k, kl, v, vl):
+        seen.append(1)
+        if len(seen) == 100:  # a writer commits txn 21 into meta page 0
+            with open(fn, "r+b") as f:
+                f.seek(16 + 24 + 96 + 8)
+                f.write(struct.pack("<Q", 21))
+        return 0
+
+    st = L.lib().hb_lmdb_scan(os.fsencode(fn), None, b"", 0, L.KV_VISIT(cb), None, None)
+    assert st == L.HB_ESTATE and b"committed to during the snapshot" in L.lib().hb_last_error()
+    assert len(seen) == len(pairs)
+    # a visitor may stop the scan
+    fn = w.save(str(tmp_path / "env2"), txnid=20)
+    st = L.lib().hb_lmdb_scan(os.fsencode(fn), None, b"", 0, L.KV_VISIT(lambda *a: 1), None, None)
+    assert st == L.HB_ESTATE
+
+
+def _write_env(tmp_path, dbs, name=None, **kw):
+    """dbs = {index: OracleDb}: all indexes share one LMDB database, like hannoy's u16 index prefix allows."""
+    pairs = []
+    for index, db in dbs.items():
+        pairs += [(bytes(k), bytes(v)) for k, v in db.export_kv(index)]
+    pairs.sort()
+    w = LmdbWriter(**kw)
+    if name:
+        w.put_named(name, pairs)
+        w.put_named("zz-other", _random_pairs(100, seed=1))
+    else:
+        w.put_unnamed(pairs)
+    return w.save(str(tmp_path / "env"))
+
+
+@pytest.mark.parametrize("metric,dims", [("cosine", 768), ("euclidean", 40), ("hamming", 70), ("binary quantized cosine", 1024)])
+def test_push_lmdb_decodes_the_index(tmp_path, metric, dims):
+    """hb_index_push_lmdb + the host half of finalize reproduce what the Writer stored (768-d f32 items are 3 077-byte
+    values: every one of them lives on overflow pages)."""
+    n = 400
+    ids = np.sort(np.random.default_rng(8).choice(1 << 28, n, replace=False)).astype(np.uint32)
+    db, x = make_db(metric, n, dims, seed=2, ids=ids)
+    db2, _ = make_db(metric, 60, dims, seed=3)
+    _write_env(tmp_path, {0: db2, 3: db, 4: db2, 0x0103: db2}, name="vecs", fill=0.75)
+    lib = L.lib()
+    mid = hb.reader._distance_of(metric).ID
+    h = C.c_void_p()
+    assert lib.hb_index_begin(mid, 3, C.byref(h)) == L.HB_OK
+    npairs = C.c_uint64()
+    st = lib.hb_index_push_lmdb(h, os.fsencode(str(tmp_path / "env")), b"vecs", C.byref(npairs))
+    assert st == L.HB_OK, lib.hb_last_error()
+    assert npairs.value == len(db.export_kv(3))          # only index 3's key range was visited
+    st = lib.hb_index_finalize(h, 0)
+    assert st in (L.HB_OK, L.HB_ECUDA), lib.hb_last_error()
+    assert lib.hb_index_n_items(h) == n and lib.hb_index_dimensions(h) == dims
+    assert lib.hb_index_max_level(h) == db.max_level and lib.hb_index_n_entry_points(h) == len(db.entry_points)
+    got = np.zeros(n, np.uint32)
+    lib.hb_index_item_ids(h, got.ctypes.data_as(C.c_void_p), n)
+    assert np.array_equal(got, ids)
+    v = np.zeros(dims, np.float32)
+    for s in (0, 200, n - 1):
+        assert lib.hb_index_item_vector(h, int(ids[s]), v.ctypes.data_as(C.c_void_p)) == L.HB_OK
+        if metric in ("euclidean", "cosine"):
+            assert np.array_equal(v, x[s])
+        elif metric == "hamming":
+            assert np.array_equal(v, (x[s] > 0).astype(np.float32))
+        else:
+            assert np.array_equal(v, np.where(np.signbit(x[s]), -1.0, 1.0).astype(np.float32))
+    lib.hb_index_free(h)
+    # Reader::open errors surface through the path route too
+    h = C.c_void_p()
+    assert lib.hb_index_open_lmdb(os.fsencode(str(tmp_path / "env")), b"vecs", mid, 9, 0, C.byref(h)) == L.HB_EMISSING_METADATA
+    assert lib.hb_index_open_lmdb(os.fsencode(str(tmp_path / "env")), b"vecs", (mid + 1) % 7, 3, 0, C.byref(h)) == L.HB_EUNMATCHING_DISTANCE
+    with pytest.raises(hb.MissingMetadata):
+        hb.Reader.open_path(str(tmp_path / "env"), 9, metric, db_name="vecs")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("metric,dims,named", [("cosine", 768, True), ("euclidean", 128, False), ("hamming", 256, False),
+                                                ("binary quantized cosine", 1024, True)])
+def test_open_path_search_equals_oracle(tmp_path, metric, dims, named):
+    n = 2500
+    ids = np.sort(np.random.default_rng(5).choice(1 << 26, n, replace=False)).astype(np.uint32)
+    db, x = make_db(metric, n, dims, seed=12, kind="clustered", ids=ids)
+    other, _ = make_db(metric, 100, dims, seed=13)
+    path = _write_env(tmp_path, {6: other, 7: db, 8: other}, name="hannoy" if named else None)
+    rd = hb.Reader.open_path(path if not named else os.path.dirname(path), 7, metric, db_name="hannoy" if named else None)
+    assert rd.n_items() == n and rd.dimensions() == dims
+    q = make_vectors(96, dims, seed=3, kind="clustered")
+    q[:6] = x[:6]
+    for count, ef in [(10, 64), (100, 100)]:
+        want = db.search_by_vector(q, count, ef=ef, counters=True)
+        got = rd.nns(count).ef_search(ef).by_vectors_raw(q, counters=True)
+        assert_same(got, want, f"lmdb route {metric}")
+        assert np.array_equal(got[3][:, :6], want[3][:, :6])
+    items = np.array([ids[0], ids[17], ids[-1], ids[-1] + 1], np.uint32)
+    assert_same(rd.nns(5).by_items_raw(items), db.search_by_item(items, 5, ef=100), "lmdb route by_item")
