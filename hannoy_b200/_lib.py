@@ -14,23 +14,26 @@ HB_OK, HB_EINVAL, HB_EDIM, HB_EFORMAT, HB_ECUDA, HB_ENOMEM, HB_ENCCL = range(7)
 HB_EMISSING_METADATA, HB_EUNMATCHING_DISTANCE, HB_ENEED_BUILD, HB_ESTATE = 7, 8, 9, 10
 HB_N_CTR = 8
 CTR_DIST_UPPER, CTR_DIST_L0, CTR_EXP_UPPER, CTR_EXP_L0, CTR_DEG_UPPER, CTR_DEG_L0, CTR_FLAGS = range(7)
-FLAG_FALLBACK, FLAG_LINEAR, FLAG_SLOW_PATH = 1, 2, 4
+FLAG_FALLBACK, FLAG_LINEAR, FLAG_SLOW_PATH, FLAG_CANCELLED = 1, 2, 4, 8
+LEN_CANCELLED, LEN_NONE = 0x80000000, 0xFFFFFFFF
 
 # every symbol include/hannoy_b200.h declares
 EXPORTS = [
     "hb_metric_name", "hb_metric_from_name", "hb_index_begin", "hb_index_push_kv", "hb_index_push_lmdb", "hb_index_open_lmdb",
-    "hb_lmdb_scan", "hb_index_from_arrays",
+    "hb_lmdb_scan", "hb_index_save", "hb_index_load", "hb_index_from_arrays",
     "hb_index_finalize", "hb_index_free", "hb_index_dimensions", "hb_index_n_items", "hb_index_n_entry_points",
     "hb_index_max_level", "hb_index_version", "hb_index_item_ids", "hb_index_contains_item", "hb_index_item_vector",
     "hb_search_by_vector", "hb_search_by_item", "hb_search_by_vector_device", "hb_exact_knn", "hb_merge_topk_device",
     "hb_launch_count", "hb_last_error", "hb_tune", "hb_debug_phases", "hb_debug_trace",
-    "hb_shard_group_create", "hb_shard_group_connect", "hb_search_sharded_device", "hb_shard_group_free",
+    "hb_cancel_token_create", "hb_cancel_token_cancel", "hb_cancel_token_reset", "hb_cancel_token_is_cancelled",
+    "hb_cancel_token_free", "hb_shard_group_create", "hb_shard_group_connect", "hb_search_sharded_device", "hb_shard_group_free",
 ]
 
 
 class QueryOpts(C.Structure):
     _fields_ = [("candidates", C.c_void_p), ("n_candidates", C.c_uint64), ("has_candidates", C.c_int),
-                ("linear_below", C.c_uint32), ("linear_below_ratio", C.c_float)]
+                ("linear_below", C.c_uint32), ("linear_below_ratio", C.c_float),
+                ("cancel", C.c_void_p), ("cancel_after_polls", C.c_uint64)]
 
 
 KV_VISIT = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_ubyte), C.c_size_t, C.POINTER(C.c_ubyte), C.c_size_t)
@@ -53,6 +56,7 @@ def lib():
         "hb_metric_name": (C.c_char_p, [i32]), "hb_metric_from_name": (i32, [C.c_char_p]),
         "hb_index_begin": (i32, [i32, u16, C.POINTER(vp)]),
         "hb_index_push_kv": (i32, [vp, C.c_char_p, sz, C.c_char_p, sz]),
+        "hb_index_save": (i32, [vp, C.c_char_p]), "hb_index_load": (i32, [vp, C.c_char_p]),
         "hb_index_push_lmdb": (i32, [vp, C.c_char_p, C.c_char_p, C.POINTER(u64)]),
         "hb_index_open_lmdb": (i32, [C.c_char_p, C.c_char_p, i32, u16, i32, C.POINTER(vp)]),
         "hb_lmdb_scan": (i32, [C.c_char_p, C.c_char_p, C.c_char_p, sz, KV_VISIT, vp, C.POINTER(u64)]),
@@ -68,6 +72,8 @@ def lib():
         "hb_search_by_vector_device": (i32, [vp, vp, u64, u32, u32, vp, vp, vp, vp, vp]),
         "hb_exact_knn": (i32, [vp, vp, u64, u32, u32, vp, vp]),
         "hb_merge_topk_device": (i32, [i32, vp, vp, u32, u64, u32, vp, vp, vp, vp]),
+        "hb_cancel_token_create": (i32, [i32, C.POINTER(vp)]), "hb_cancel_token_cancel": (i32, [vp]),
+        "hb_cancel_token_reset": (i32, [vp]), "hb_cancel_token_is_cancelled": (i32, [vp]), "hb_cancel_token_free": (None, [vp]),
         "hb_shard_group_create": (i32, [i32, i32, i32, u64, u32, C.POINTER(vp), vp]),
         "hb_shard_group_connect": (i32, [vp, vp]),
         "hb_search_sharded_device": (i32, [vp, vp, vp, u64, u32, u32, vp, vp, vp, vp]),

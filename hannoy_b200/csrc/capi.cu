@@ -167,6 +167,40 @@ hb_status hb_index_open_lmdb(const char* path, const char* db_name, hb_metric m,
     return st;
 }
 
+// ---- flat-file snapshot cache (snapshot.cpp) ----------------------------------------------------------------------
+hb_status hb_index_save(const hb_index* ix, const char* path) {
+    if (!ix || !path) { set_error("hb_index_save: null argument"); return HB_EINVAL; }
+    if (!ix->finalized && (ix->ids.empty() || !ix->kv_items.empty() || !ix->kv_links.empty())) {
+        set_error("hb_index_save: the index holds no decoded snapshot yet (finalize it first)");
+        return HB_ESTATE;
+    }
+    try {
+        return snapshot_save(ix, path);
+    } catch (const std::bad_alloc&) {
+        return HB_ENOMEM;
+    }
+}
+
+hb_status hb_index_load(hb_index* ix, const char* path) {
+    if (!ix || !path) { set_error("hb_index_load: null argument"); return HB_EINVAL; }
+    if (ix->finalized || !ix->ids.empty() || ix->have_metadata) { set_error("hb_index_load: the index is not empty"); return HB_ESTATE; }
+    FILE* f = fopen(path, "rb");
+    if (!f) { set_error("snapshot: cannot open %s", path); return HB_EINVAL; }
+    hb_status st = HB_OK;
+    try {
+        fseek(f, 0, SEEK_END);
+        long sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        std::vector<uint8_t> buf(sz > 0 ? (size_t)sz : 0);
+        if (!buf.empty() && fread(buf.data(), 1, buf.size(), f) != buf.size()) { set_error("snapshot: short read on %s", path); st = HB_EINVAL; }
+        if (st == HB_OK) st = snapshot_load(ix, buf.data(), buf.size());
+    } catch (const std::bad_alloc&) {
+        st = HB_ENOMEM;
+    }
+    fclose(f);
+    return st;
+}
+
 hb_status hb_index_from_arrays(hb_index* ix, uint32_t dims, const uint32_t* ids, uint64_t n, const void* rows,
                                const float* hdr, uint32_t n_layers, const uint64_t* const* offsets,
                                const uint32_t* const* nbrs, const uint32_t* entry_points, uint32_t n_ep,
@@ -516,6 +550,14 @@ static bool should_linear_scan(size_t n_items, size_t cand_in_db, const hb_query
     return below_threshold && below_ratio;
 }
 
+struct hb_cancel_token {
+    int device = 0;
+    uint32_t* d_flag = nullptr;   // polled by the search kernels
+    uint32_t* h_vals = nullptr;   // pinned {1, 0}: sources of the flag copies
+    cudaStream_t stream = nullptr;  // non-blocking: the copy overtakes running kernels
+    std::atomic<int> cancelled{0};
+};
+
 static hb_status search_host(const hb_index* ix, const float* q, const uint32_t* items, uint64_t nq, uint32_t count, uint32_t ef,
                              const hb_query_opts* opts, uint32_t* out_ids, float* out_dist, uint32_t* out_len, uint64_t* out_ctr) {
     const bool by_item = items != nullptr;
@@ -537,6 +579,19 @@ static hb_status search_host(const hb_index* ix, const float* q, const uint32_t*
     }
     if (n == 0 || (has_cand && ci.slots.empty())) { none(by_item ? 0xffffffffu : 0u); return HB_OK; }
     bool linear = has_cand && should_linear_scan(n, ci.slots.size(), opts);
+    const hb_cancel_token* tok = opts ? opts->cancel : nullptr;
+    const uint64_t cancel_after = opts ? opts->cancel_after_polls : 0;
+    if (tok && tok->device != ix->device) { set_error("the cancel token lives on device %d, the index on %d", tok->device, ix->device); return HB_EINVAL; }
+    int linear_cancelled = 0;
+    std::vector<uint32_t> scan_slots;  // linear scan under a poll budget: cancel_fn is called once per candidate id,
+    if (linear && cancel_after) {      // present or not (reader.rs:683-687) -> the scan stops before candidate number cancel_after
+        std::vector<uint32_t> c(opts->candidates, opts->candidates + opts->n_candidates);
+        std::sort(c.begin(), c.end());
+        c.erase(std::unique(c.begin(), c.end()), c.end());
+        if (c.size() >= cancel_after) { c.resize(cancel_after - 1); linear_cancelled = 1; }
+        for (uint32_t id : c) { int64_t s = slot_of(ix, id); if (s >= 0) scan_slots.push_back((uint32_t)s); }
+    }
+    const std::vector<uint32_t>& lin_slots = (linear && cancel_after) ? scan_slots : ci.slots;
     if (count == 0 && !by_item) { none(0); return HB_OK; }
 
     CUDA_TRY(cudaSetDevice(ix->device));
@@ -566,17 +621,20 @@ static hb_status search_host(const hb_index* ix, const float* q, const uint32_t*
         ci.bits.assign(words, 0);
         for (uint32_t s : ci.slots) ci.bits[s >> 5] |= 1u << (s & 31);
         size_t cb = words * 4, off_slots = (cb + 255) & ~(size_t)255;
-        if ((st = grow(&w->d_cand, &w->d_cand_bytes, off_slots + ci.slots.size() * 4 + 256)) != HB_OK) return fail(st);
+        if ((st = grow(&w->d_cand, &w->d_cand_bytes, off_slots + lin_slots.size() * 4 + 256)) != HB_OK) return fail(st);
         cudaMemcpyAsync(w->d_cand, ci.bits.data(), cb, cudaMemcpyHostToDevice, stream);
-        cudaMemcpyAsync((uint8_t*)w->d_cand + off_slots, ci.slots.data(), ci.slots.size() * 4, cudaMemcpyHostToDevice, stream);
+        if (!lin_slots.empty()) cudaMemcpyAsync((uint8_t*)w->d_cand + off_slots, lin_slots.data(), lin_slots.size() * 4, cudaMemcpyHostToDevice, stream);
         p.cand_bits = (const uint32_t*)w->d_cand;
         p.cand_slots = (const uint32_t*)((uint8_t*)w->d_cand + off_slots);
-        p.n_cand_slots = (uint32_t)ci.slots.size();
+        p.n_cand_slots = (uint32_t)lin_slots.size();
     }
     p.q = by_item ? nullptr : (const float*)w->d_q;
     p.q_slots = by_item ? (const uint32_t*)w->d_q : nullptr;
     p.nq = nq; p.count = count; p.ef_raw = ef;
     p.mode = (by_item ? 1 : 0) | (linear ? 2 : 0);
+    p.cancel_flag = tok ? tok->d_flag : nullptr;
+    p.cancel_after = (uint32_t)std::min<uint64_t>(cancel_after, 0xffffffffull);
+    p.linear_cancelled = linear_cancelled;
     uint8_t* ob = (uint8_t*)w->d_out;
     p.out_ids = (uint32_t*)ob; p.out_dist = (float*)(ob + off_dist); p.out_len = (uint32_t*)(ob + off_len);
     p.out_ctr = out_ctr ? (uint64_t*)(ob + off_ctr) : nullptr;
@@ -595,6 +653,47 @@ static hb_status search_host(const hb_index* ix, const float* q, const uint32_t*
 }
 
 extern "C" {
+
+hb_status hb_cancel_token_create(int device, hb_cancel_token** out) {
+    if (!out) { set_error("hb_cancel_token_create: null argument"); return HB_EINVAL; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device available (libhannoy_b200 has no CPU path)"); return HB_ECUDA; }
+    if (device < 0 || device >= ndev) { set_error("bad device %d", device); return HB_EINVAL; }
+    CUDA_TRY(cudaSetDevice(device));
+    hb_cancel_token* t = new (std::nothrow) hb_cancel_token();
+    if (!t) return HB_ENOMEM;
+    t->device = device;
+    if (cudaMalloc(&t->d_flag, 4) != cudaSuccess || cudaMemset(t->d_flag, 0, 4) != cudaSuccess ||
+        cudaHostAlloc(&t->h_vals, 8, cudaHostAllocDefault) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("cancel token: %s", cudaGetErrorString(cudaGetLastError()));
+        hb_cancel_token_free(t);
+        return HB_ECUDA;
+    }
+    t->h_vals[0] = 1; t->h_vals[1] = 0;
+    *out = t;
+    return HB_OK;
+}
+static hb_status token_write(hb_cancel_token* t, int v) {
+    if (!t) { set_error("null cancel token"); return HB_EINVAL; }
+    t->cancelled.store(v);
+    CUDA_TRY(cudaSetDevice(t->device));
+    CUDA_TRY(cudaMemcpyAsync(t->d_flag, &t->h_vals[v ? 0 : 1], 4, cudaMemcpyHostToDevice, t->stream));
+    CUDA_TRY(cudaStreamSynchronize(t->stream));  // the copy engine runs beside the kernels: this returns in microseconds
+    return HB_OK;
+}
+hb_status hb_cancel_token_cancel(hb_cancel_token* t) { return token_write(t, 1); }
+hb_status hb_cancel_token_reset(hb_cancel_token* t) { return token_write(t, 0); }
+int hb_cancel_token_is_cancelled(const hb_cancel_token* t) { return t ? t->cancelled.load() : 0; }
+void hb_cancel_token_free(hb_cancel_token* t) {
+    if (!t) return;
+    cudaSetDevice(t->device);
+    if (t->stream) cudaStreamDestroy(t->stream);
+    if (t->d_flag) cudaFree(t->d_flag);
+    if (t->h_vals) cudaFreeHost(t->h_vals);
+    delete t;
+}
 
 hb_status hb_search_by_vector(const hb_index* ix, const float* q, uint64_t nq, uint32_t dims, uint32_t count, uint32_t ef,
                               const hb_query_opts* opts, uint32_t* out_ids, float* out_dist, uint32_t* out_len,

@@ -91,6 +91,13 @@ struct SearchParams {
     uint32_t* peer_ids[HB_MAX_SHARDS] = {};
     float* peer_dist[HB_MAX_SHARDS] = {};
     int n_peers = 0, shard_rank = 0;
+    // cancellation (reader.rs:91-188,330): `cancel_fn` is polled before every pop of a layer-0 visit and before every
+    // linear-scan chunk.  cancel_flag = device word set asynchronously by hb_cancel_token_cancel; cancel_after = the
+    // deterministic closure "true from its cancel_after-th call on" (0 = never; dead-entry pruning is then off so
+    // that the poll count equals the reference's); linear_cancelled = the host already cut the linear scan short.
+    const uint32_t* cancel_flag = nullptr;
+    uint32_t cancel_after = 0;
+    int linear_cancelled = 0;
     int defer = 1;                     // layer 0, pass 0: overlap a chunk's heap update with the next pop's adjacency / visited traffic
 };
 #ifndef HB_ROW_GROUP
@@ -172,6 +179,8 @@ hb_status decode_kv(hb_index* ix, const uint8_t* key, size_t klen, const uint8_t
 hb_status build_host_snapshot_from_kv(hb_index* ix);
 bool roaring_decode(const uint8_t* p, size_t len, std::vector<uint32_t>& out);
 int64_t slot_of(const hb_index* ix, uint32_t id);
+hb_status snapshot_save(const hb_index* ix, const char* path);
+hb_status snapshot_load(hb_index* ix, const uint8_t* data, size_t size);
 // lmdb_walk.cpp: in-order walk of one database of an LMDB data file, restricted to keys starting with `prefix`
 typedef hb_status (*lmdb_visit_fn)(void* user, const uint8_t* key, size_t klen, const uint8_t* val, size_t vlen, unsigned node_flags);
 hb_status lmdb_scan(const char* path, const char* db_name, const uint8_t* prefix, size_t prefix_len, lmdb_visit_fn fn, void* user,

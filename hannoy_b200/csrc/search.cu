@@ -72,6 +72,8 @@ struct Ctx {
     const float* qs; float qn;            // query (device layout) in shared memory, query header norm
     uint32_t excl;                        // by_item: slot removed from the candidates, else UINT32_MAX
     bool overflow;
+    bool cancelled;                       // the visit in progress returned Completion::Cancelled(res)
+    uint32_t polls;                       // calls of cancel_fn made by this query so far
     bool tr;                              // this warp writes the event trace (HB_TRACE builds)
     RowRing& ring;                        // per-warp, lives across queries (barrier phases persist)
 #ifdef HB_PHASES
@@ -84,12 +86,25 @@ struct Ctx {
 
 __device__ __forceinline__ float key_dist(u64 k) { return __uint_as_float((uint32_t)(k >> 32)); }
 
+// `cancel_fn()` — reader.rs:330.  cancel_next: would the next call return true (no call is made);
+// cancel_poll: the call itself.
+__device__ __forceinline__ bool cancel_flag_set(const Ctx& c) {
+    return c.p.cancel_flag && *reinterpret_cast<const volatile uint32_t*>(c.p.cancel_flag) != 0;
+}
+__device__ __forceinline__ bool cancel_next(const Ctx& c) {
+    return (c.p.cancel_after && c.polls + 1 >= c.p.cancel_after) || cancel_flag_set(c);
+}
+__device__ __forceinline__ bool cancel_poll(Ctx& c) {
+    ++c.polls;
+    return (c.p.cancel_after && c.polls >= c.p.cancel_after) || cancel_flag_set(c);
+}
+
 // ---- one-by-one heap updates: the fallback for heaps of more than 32 * MERGE_TILES entries (large ef, pass 1) ----
 // Kept out of line (cold): it works on a copy of the heap state so that Ctx never has its address taken.
 struct Heaps {
     u64* res; int res_len, res_cap;
     u64* que; int q_len, q_cap;
-    int pass; bool overflow;
+    int pass; bool overflow;  // pass != 0: never prune (also set for the poll-exact cancellation mode)
 };
 // res.push (unconditional)
 __device__ __forceinline__ void res_push(Heaps& c, u64 key) {
@@ -343,7 +358,7 @@ __device__ __forceinline__ void heaps_stage_res(Ctx& c, ChunkUpdate& u, int ef) 
         if (m_res) c.res_len = merge_batch<false, false, MERGE_TILES>(c.res, c.res_len, u.acc && u.pf, ((u64)u.bits << 32) | u.s, target, 0u);
     } else {
         const unsigned accm = __ballot_sync(FULL, u.acc && !u.qskip);
-        Heaps h{c.res, c.res_len, c.res_cap, c.que, c.q_len, c.q_cap, c.p.pass, false};
+        Heaps h{c.res, c.res_len, c.res_cap, c.que, c.q_len, c.q_cap, c.p.pass | (int)c.p.cancel_after, false};
         heaps_update_seq(&h, u.mode, ef, resm, accm, u.bits, u.s);
         c.res_len = h.res_len;
         c.q_len = h.q_len;
@@ -356,7 +371,7 @@ __device__ __forceinline__ void heaps_stage_queue(Ctx& c, const ChunkUpdate& u, 
     const int lane = lane_id();
     // Entries that can never be popped (is_dead, judged against the UPDATED result set) are not pushed, and old
     // ones — they sit at the front of the descending array — are trimmed in the same pass.
-    const bool prune = c.p.pass == 0 && c.res_len >= ef && c.res_len > 0 && !(c.res[c.res_len - 1] >> 63);
+    const bool prune = c.p.pass == 0 && !c.p.cancel_after && c.res_len >= ef && c.res_len > 0 && !(c.res[c.res_len - 1] >> 63);
     const uint32_t mb = prune ? (uint32_t)(c.res[c.res_len - 1] >> 32) : 0xffffffffu;
     const bool qhas = u.acc && !u.qskip && !(prune && !(u.bits >> 31) && u.bits > mb);
     const int mq = __popc(__ballot_sync(FULL, qhas));
@@ -387,7 +402,7 @@ __device__ __forceinline__ void heaps_stage_queue(Ctx& c, const ChunkUpdate& u, 
 // stages, which hide their latency.  When the bound does not settle it, the pending update is applied first and
 // the reference's order is followed literally.
 template <int KIND>
-__device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_eps, uint32_t single, uint32_t level, int ef, bool filt, bool linear) {
+__device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_eps, uint32_t single, uint32_t level, int ef, bool filt, bool linear, bool can_cancel) {
     const DevIndex& ix = c.p.ix;
     const int lane = lane_id();
     const int l01 = level ? 0 : 1;
@@ -415,6 +430,7 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
         PH_DECL
         if (base0 < n_first && !c.overflow) {
             if (pend) { heaps_stage_res(c, u, ef); heaps_stage_queue(c, u, ef); pend = false; if (c.overflow) break; }
+            if (linear && can_cancel && cancel_flag_set(c)) { c.cancelled = true; break; }  // reader.rs:684-687, per chunk
             valid = base0 + lane < n_first;
             s = !valid ? 0 : (list ? __ldg(&list[base0 + lane]) : single);
             base0 += 32;
@@ -422,7 +438,7 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
         } else {
             mode = CH_NBR;
             bool have = false;
-            if (pend && defer && csr_pos >= csr_end) {
+            if (pend && defer && csr_pos >= csr_end && !(can_cancel && cancel_next(c))) {
                 // ---- decide the next pop before the pending update is applied ----
                 const u64 qk = u.acc ? (((u64)u.bits << 32) | (uint32_t)(~u.s)) : NONE;
                 const u64 cand_new = warp_min_u64(qk);
@@ -442,6 +458,7 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
                         u.qskip = !from_old && qk == nx;
                         const uint32_t cs = ~(uint32_t)nx;
                         c.cur_exp += 1;
+                        if (can_cancel) ++c.polls;                 // the call that precedes this pop returned false
                         TR(c, TR_POP)
                         uint32_t a = (cs == spec_cs) ? spec_adj : __ldg(&nbrx[(size_t)cs * FIXED_DEG + lane]);
                         heaps_stage_res(c, u, ef);                 // ... while the adjacency line is on its way
@@ -475,6 +492,7 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
                 if (c.overflow || linear) break;
                 if (csr_pos >= csr_end) {
                     if (c.q_len == 0) break;
+                    if (can_cancel && cancel_poll(c)) { c.cancelled = true; break; }  // reader.rs:330-332
                     u64 top = c.que[c.q_len - 1];
                     float f = key_dist(top);
                     f_max = c.res_len ? key_dist(c.res[c.res_len - 1]) : FLT_MAX;
@@ -663,6 +681,7 @@ __device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64*
     c.touched = p.touched + (size_t)slot_idx * p.touched_cap;
     c.touched_len = 0; c.touched_over = false;
     c.excl = 0xffffffffu; c.overflow = false;
+    c.cancelled = false; c.polls = 0;
     c.tr = false;
 #ifdef HB_TRACE
     c.tr = slot_idx == 777 && p.pass == 0;
@@ -718,8 +737,9 @@ __device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64*
             if (st == ST_UPPER) { ef = 1; filt = false; }
             else if (st == ST_L0) { ef = ef0; level = 0; TR(c, TR_L0) }
             else if (st == ST_LIN) { ef = (int)count; level = 0; filt = false; }
-            visit<KIND>(c, eps, ix.n_ep, ep_single, level, ef, filt, st == ST_LIN);
-            if (c.overflow || st == ST_LIN) break;
+            visit<KIND>(c, eps, ix.n_ep, ep_single, level, ef, filt, st == ST_LIN,
+                        st != ST_UPPER && (p.cancel_flag != nullptr || p.cancel_after != 0));
+            if (c.overflow || c.cancelled || st == ST_LIN) break;
             if (st == ST_UPPER) {
                 bool found = c.res_len != 0;       // reference: expect("No neighbor was found")
                 if (found) { ep_single = (uint32_t)c.res[0]; eps = nullptr; }  // peek_min
@@ -752,11 +772,18 @@ __device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64*
             c.res = base_res + acc_len;
             c.res_cap = base_cap - acc_len;
         }
-        c.res = base_res; c.res_cap = base_cap;
-        if (first >= 0) {
-            c.res_len = acc_len;
-            if (!c.overflow) sort_tail(c.res, first, acc_len);
+        if (c.cancelled && !c.overflow) {
+            // return_if_cancelled! (reader.rs:749-764,844-859): only the interrupted visit's heap, ascending, take(count)
+            flags |= HB_FLAG_CANCELLED;
+            c.res_cap = base_cap - (int)(c.res - base_res);
+        } else {
+            c.res = base_res; c.res_cap = base_cap;
+            if (first >= 0) {
+                c.res_len = acc_len;
+                if (!c.overflow) sort_tail(c.res, first, acc_len);
+            }
         }
+        if (p.linear_cancelled) flags |= HB_FLAG_CANCELLED;
         n_out = min(c.res_len, (int)count);
         vis_clear(c);
     }
@@ -790,7 +817,7 @@ __device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64*
         }
     }
     if (lane == 0) {
-        p.out_len[qi] = (uint32_t)n_out;
+        p.out_len[qi] = (uint32_t)n_out | ((flags & HB_FLAG_CANCELLED) ? HB_LEN_CANCELLED : 0u);
         if (p.out_ctr) {
             uint64_t* o = p.out_ctr + qi * HB_N_CTR;
             o[HB_CTR_DIST_UPPER] = c.n_dist_up; o[HB_CTR_DIST_L0] = c.n_dist_l0;

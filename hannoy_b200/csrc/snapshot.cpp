@@ -244,6 +244,144 @@ hb_status build_host_snapshot_from_kv(hb_index* ix) {
     return HB_OK;
 }
 
+// ---- flat-file snapshot cache ------------------------------------------------------------------------------------
+// The decoded host snapshot (what hb_index_finalize uploads) written as one flat little-endian file, so that a restart
+// does not walk LMDB and decode a roaring bitmap per node again.  The reference has no counterpart (its Reader reads
+// LMDB lazily, reader.rs:951-976); the file is a cache, valid for as long as the caller's key for it (environment path,
+// index, LMDB transaction id from hb_lmdb_scan, the index Version of version.rs) is unchanged.
+//   header : "HB2SNAP1" | u32 metric | u32 index | u32 dims | u32 max_level | u64 n | u32 n_layers | u32 n_eps |
+//            u32 version[3] | u32 row_bytes | u64 nnz[n_layers]
+//   body   : ids u32[n] | hdr f32[n] | eps u32[n_eps] (slots) | per layer: off u64[n+1], nbr u32[nnz] (slots) |
+//            pad to 8 | rows u8[n * row_bytes]
+//   trailer: u64 FNV-1a over every preceding 8-byte word
+namespace {
+struct Fnv {
+    uint64_t h = 0xcbf29ce484222325ull;
+    uint8_t carry[8];
+    size_t nc = 0;
+    void word(uint64_t w) { h = (h ^ w) * 0x100000001b3ull; }
+    void feed(const void* p, size_t len) {
+        const uint8_t* b = (const uint8_t*)p;
+        while (len && nc) { carry[nc++] = *b++; --len; if (nc == 8) { uint64_t w; std::memcpy(&w, carry, 8); word(w); nc = 0; } }
+        for (; len >= 8; len -= 8, b += 8) { uint64_t w; std::memcpy(&w, b, 8); word(w); }
+        while (len) { carry[nc++] = *b++; --len; }
+    }
+    uint64_t finish() { if (nc) { std::memset(carry + nc, 0, 8 - nc); uint64_t w; std::memcpy(&w, carry, 8); word(w); nc = 0; } return h; }
+};
+struct Writer {
+    FILE* f; Fnv fnv; bool ok = true;
+    void put(const void* p, size_t len) { if (len && ok) { ok = fwrite(p, 1, len, f) == len; fnv.feed(p, len); } }
+    template <class T> void val(T v) { put(&v, sizeof(T)); }
+};
+struct Cursor {
+    const uint8_t* p; size_t left; bool ok = true;
+    const uint8_t* take(size_t len) { if (len > left) { ok = false; return nullptr; } const uint8_t* r = p; p += len; left -= len; return r; }
+    template <class T> T val() { T v{}; const uint8_t* r = take(sizeof(T)); if (r) std::memcpy(&v, r, sizeof(T)); return v; }
+    template <class T> bool vec(std::vector<T>& out, size_t count) {
+        if (count > left / sizeof(T)) { ok = false; return false; }
+        const uint8_t* r = take(count * sizeof(T));
+        out.resize(count);
+        if (count) std::memcpy(out.data(), r, count * sizeof(T));
+        return true;
+    }
+};
+const char kSnapMagic[8] = {'H', 'B', '2', 'S', 'N', 'A', 'P', '1'};
+}  // namespace
+
+hb_status snapshot_save(const hb_index* ix, const char* path) {
+    std::string tmp = std::string(path) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) { set_error("snapshot: cannot create %s", tmp.c_str()); return HB_EINVAL; }
+    Writer w{f};
+    const uint64_t n = ix->ids.size();
+    w.put(kSnapMagic, 8);
+    w.val<uint32_t>((uint32_t)ix->metric); w.val<uint32_t>(ix->index); w.val<uint32_t>(ix->dims); w.val<uint32_t>(ix->max_level);
+    w.val<uint64_t>(n); w.val<uint32_t>((uint32_t)ix->layers.size()); w.val<uint32_t>((uint32_t)ix->eps.size());
+    for (int i = 0; i < 3; ++i) w.val<uint32_t>(ix->version[i]);
+    w.val<uint32_t>((uint32_t)ix->host_row_bytes);
+    for (const HostLayer& hl : ix->layers) w.val<uint64_t>(hl.nbr.size());
+    w.put(ix->ids.data(), n * 4);
+    w.put(ix->host_hdr.data(), n * 4);
+    w.put(ix->eps.data(), ix->eps.size() * 4);
+    size_t body = n * 8 + ix->eps.size() * 4;
+    for (const HostLayer& hl : ix->layers) {
+        std::vector<uint64_t> zero;
+        const std::vector<uint64_t>& off = hl.off.size() == n + 1 ? hl.off : (zero.assign(n + 1, 0), zero);
+        w.put(off.data(), (n + 1) * 8);
+        w.put(hl.nbr.data(), hl.nbr.size() * 4);
+        body += hl.nbr.size() * 4;
+    }
+    const uint8_t pad[8] = {};
+    w.put(pad, (8 - body % 8) % 8);
+    w.put(ix->host_rows.data(), n * ix->host_row_bytes);
+    uint64_t sum = w.fnv.finish();
+    bool ok = w.ok && fwrite(&sum, 1, 8, f) == 8;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); set_error("snapshot: writing %s failed", path); return HB_EINVAL; }
+    return HB_OK;
+}
+
+hb_status snapshot_load(hb_index* ix, const uint8_t* data, size_t size) {
+    if (size < 8 + 8 || std::memcmp(data, kSnapMagic, 8)) { set_error("snapshot: not a hannoy_b200 snapshot file"); return HB_EFORMAT; }
+    Fnv fnv;
+    fnv.feed(data, size - 8);
+    uint64_t want;
+    std::memcpy(&want, data + size - 8, 8);
+    if (fnv.finish() != want) { set_error("snapshot: checksum mismatch (truncated or corrupt file)"); return HB_EFORMAT; }
+    Cursor c{data + 8, size - 16};
+    uint32_t metric = c.val<uint32_t>(), index = c.val<uint32_t>(), dims = c.val<uint32_t>(), max_level = c.val<uint32_t>();
+    uint64_t n = c.val<uint64_t>();
+    uint32_t n_layers = c.val<uint32_t>(), n_eps = c.val<uint32_t>();
+    uint32_t ver[3];
+    for (int i = 0; i < 3; ++i) ver[i] = c.val<uint32_t>();
+    uint32_t row_bytes = c.val<uint32_t>();
+    if (!c.ok) { set_error("snapshot: truncated header"); return HB_EFORMAT; }
+    if (metric != (uint32_t)ix->metric) {  // the same check Reader::open makes on the stored distance name (reader.rs:400-405)
+        set_error("Internal error: unmatching distance: expected `%s`, received `%s`", hb_metric_name((hb_metric)metric), hb_metric_name(ix->metric));
+        return HB_EUNMATCHING_DISTANCE;
+    }
+    if (index != ix->index) { set_error("snapshot: file holds index %u, asked for %u", index, (unsigned)ix->index); return HB_EINVAL; }
+    if (n >= 0xffffffffull || n_layers > (uint32_t)MAX_LEVELS || row_bytes != natural_row_bytes(ix->metric, dims) || (n && max_level >= n_layers)) {
+        set_error("snapshot: inconsistent header");
+        return HB_EFORMAT;
+    }
+    std::vector<uint64_t> nnz(n_layers);
+    for (uint32_t l = 0; l < n_layers; ++l) nnz[l] = c.val<uint64_t>();
+    size_t body = n * 8 + (size_t)n_eps * 4;
+    c.vec(ix->ids, n);
+    c.vec(ix->host_hdr, n);
+    c.vec(ix->eps, n_eps);
+    ix->layers.assign(n_layers, HostLayer());
+    for (uint32_t l = 0; l < n_layers && c.ok; ++l) {
+        c.vec(ix->layers[l].off, n + 1);
+        c.vec(ix->layers[l].nbr, nnz[l]);
+        body += nnz[l] * 4;
+    }
+    c.take((8 - body % 8) % 8);
+    if (c.ok && n * (uint64_t)row_bytes != c.left) c.ok = false;
+    if (c.ok) c.vec(ix->host_rows, n * (size_t)row_bytes);
+    if (!c.ok) { set_error("snapshot: sizes do not add up"); return HB_EFORMAT; }
+    // the arrays are trusted by the kernels: validate what an out-of-range value would break
+    for (uint64_t i = 1; i < n; ++i) if (ix->ids[i] <= ix->ids[i - 1]) { set_error("snapshot: ids not ascending"); return HB_EFORMAT; }
+    for (uint32_t e : ix->eps) if (e >= n) { set_error("snapshot: entry point out of range"); return HB_EFORMAT; }
+    for (uint32_t l = 0; l < n_layers; ++l) {
+        const HostLayer& hl = ix->layers[l];
+        if (hl.off[0] != 0 || hl.off[n] != hl.nbr.size()) { set_error("snapshot: layer %u offsets do not cover its edges", l); return HB_EFORMAT; }
+        for (uint64_t i = 0; i < n; ++i) if (hl.off[i + 1] < hl.off[i]) { set_error("snapshot: layer %u offsets not monotone", l); return HB_EFORMAT; }
+        for (uint32_t t : hl.nbr) if (t >= n) { set_error("snapshot: layer %u neighbour out of range", l); return HB_EFORMAT; }
+    }
+    ix->dims = dims;
+    ix->host_row_bytes = row_bytes;
+    ix->max_level = max_level;
+    for (int i = 0; i < 3; ++i) ix->version[i] = ver[i];
+    ix->have_metadata = true;
+    ix->meta_distance = hb_metric_name(ix->metric);
+    ix->meta_dims = dims;
+    ix->meta_items = ix->ids;
+    ix->meta_max_level = max_level;
+    return HB_OK;
+}
+
 // ---- device row layout -------------------------------------------------------------------------------
 int kind_for(hb_metric m, uint32_t dims) {
     if (m >= HB_HAMMING) return KIND_BIN;

@@ -131,6 +131,32 @@ class Searched:
         return f"Searched(nns={self.nns!r}, did_cancel={self.did_cancel_})"
 
 
+class CancelToken:
+    """What a `cancel_fn` closure becomes on this side of the ABI (reader.rs:91-188): a flag on the device that any host
+    thread may trip while searches carrying it are in flight (hb_cancel_token_*)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        _check(L.lib().hb_cancel_token_create(device, C.byref(self._h)))
+
+    def cancel(self):
+        _check(L.lib().hb_cancel_token_cancel(self._h))
+
+    def reset(self):
+        _check(L.lib().hb_cancel_token_reset(self._h))
+
+    def is_cancelled(self):
+        return bool(L.lib().hb_cancel_token_is_cancelled(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.lib().hb_cancel_token_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
 class QueryBuilder:
     """reader.rs:60-261"""
 
@@ -141,6 +167,8 @@ class QueryBuilder:
         self._candidates = None
         self._linear_below = DEFAULT_LINEAR_SCAN_THRESHOLD
         self._linear_below_ratio = DEFAULT_LINEAR_SCAN_THRESHOLD_RATIO
+        self._cancel = None        # CancelToken
+        self._cancel_after = 0     # deterministic cancel_fn: true from its N-th call on
 
     def ef_search(self, ef):  # reader.rs:217-220
         self.ef = max(int(ef), self.count)
@@ -167,6 +195,8 @@ class QueryBuilder:
             o.has_candidates = 1
         o.linear_below = self._linear_below
         o.linear_below_ratio = self._linear_below_ratio
+        o.cancel = self._cancel._h if self._cancel is not None else None
+        o.cancel_after_polls = self._cancel_after
         return o
 
     # -- batched forms (raw arrays) --
@@ -202,7 +232,8 @@ class QueryBuilder:
 
     @staticmethod
     def _searched(ids, dist, n):
-        return Searched([(int(ids[j]), float(dist[j])) for j in range(int(n))], False)
+        n = int(n)
+        return Searched([(int(ids[j]), float(dist[j])) for j in range(n & 0x7fffffff)], bool(n & L.LEN_CANCELLED))
 
     def by_vectors(self, vectors):
         ids, dist, lens = self.by_vectors_raw(vectors)
@@ -223,20 +254,59 @@ class QueryBuilder:
     def by_item(self, item, rtxn=None):  # reader.rs:81-89
         return self.by_items([item])[0]
 
-    def by_vector_with_cancellation(self, vector, cancel_fn=None):
-        return self.by_vector(vector)
+    def with_cancellation(self, cancel_fn):
+        """The batched spelling of *_with_cancellation: every query of the next by_vectors / by_items call polls it."""
+        self._cancel, self._cancel_after = None, 0
+        if isinstance(cancel_fn, CancelToken):
+            self._cancel = cancel_fn
+        elif isinstance(cancel_fn, int) and not isinstance(cancel_fn, bool):
+            self._cancel_after = int(cancel_fn)
+        elif cancel_fn is not None:
+            raise TypeError("pass a CancelToken, a poll count, or use by_*_with_cancellation for a callable")
+        return self
 
-    def by_item_with_cancellation(self, item, cancel_fn=None):
-        return self.by_item(item)
+    def _run_cancellable(self, cancel_fn, run):
+        """reader.rs:108-118,167-188.  `cancel_fn` is a CancelToken, an int N (the closure that turns true at its N-th
+        call: polled exactly where the reference polls), or any callable — evaluated by a watcher thread on the host
+        while the kernels run, tripping a token when it first returns True."""
+        if not callable(cancel_fn):
+            return run(self.with_cancellation(cancel_fn))
+        import threading
+        tok = CancelToken(self.reader._device)
+        done = threading.Event()
+
+        def watch():
+            while not done.is_set():
+                if cancel_fn():
+                    tok.cancel()
+                    return
+                done.wait(50e-6)
+
+        t = threading.Thread(target=watch, daemon=True)
+        t.start()
+        try:
+            return run(self.with_cancellation(tok))
+        finally:
+            done.set()
+            t.join()
+            self._cancel = None
+            tok.close()
+
+    def by_vector_with_cancellation(self, vector, cancel_fn):
+        return self._run_cancellable(cancel_fn, lambda qb: qb.by_vector(vector))
+
+    def by_item_with_cancellation(self, item, cancel_fn):
+        return self._run_cancellable(cancel_fn, lambda qb: qb.by_item(item))
 
 
 class Reader:
     """reader.rs:374-620.  Holds the HBM-resident snapshot of one hannoy index."""
 
-    def __init__(self, handle, distance, index):
+    def __init__(self, handle, distance, index, device=0):
         self._h = handle
         self._distance = distance
         self._index = index
+        self._device = device
 
     def __del__(self):
         self.close()
@@ -260,7 +330,7 @@ class Reader:
         except Exception:
             lib.hb_index_free(h)
             raise
-        return cls(h, d, index)
+        return cls(h, d, index, device)
 
     @classmethod
     def open_path(cls, path, index, distance, db_name=None, device=0):
@@ -271,7 +341,25 @@ class Reader:
         h = C.c_void_p()
         _check(L.lib().hb_index_open_lmdb(os.fsencode(path), db_name.encode() if db_name else None, d.ID, index, device,
                                           C.byref(h)))
-        return cls(h, d, index)
+        return cls(h, d, index, device)
+
+    def save(self, path):
+        """Write the decoded snapshot to a flat cache file (hb_index_save); `Reader.load` brings it back without LMDB."""
+        _check(L.lib().hb_index_save(self._h, os.fsencode(path)))
+
+    @classmethod
+    def load(cls, path, index, distance, device=0):
+        d = _distance_of(distance)
+        lib = L.lib()
+        h = C.c_void_p()
+        _check(lib.hb_index_begin(d.ID, index, C.byref(h)))
+        try:
+            _check(lib.hb_index_load(h, os.fsencode(path)))
+            _check(lib.hb_index_finalize(h, device))
+        except Exception:
+            lib.hb_index_free(h)
+            raise
+        return cls(h, d, index, device)
 
     @classmethod
     def from_arrays(cls, distance, dims, ids, rows, hdr, layers, entry_points, max_level, index=0, device=0):
@@ -301,7 +389,7 @@ class Reader:
         except Exception:
             lib.hb_index_free(h)
             raise
-        return cls(h, d, index)
+        return cls(h, d, index, device)
 
     # accessors — reader.rs:545-606
     def dimensions(self):

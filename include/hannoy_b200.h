@@ -84,6 +84,15 @@ typedef int (*hb_kv_visit)(void* user, const uint8_t* key, size_t klen, const ui
 hb_status hb_lmdb_scan(const char* path, const char* db_name, const uint8_t* prefix, size_t prefix_len, hb_kv_visit fn,
                        void* user, uint64_t* txnid_out);
 
+/* Route (c): the flat-file snapshot cache.  hb_index_save writes the decoded snapshot of a finalized index (ids, rows,
+ * header norms, per-layer CSR, entry points, the index Version of src/version.rs) to `path` (atomically: tmp + rename,
+ * FNV-1a trailer); hb_index_load fills an index created by hb_index_begin from such a file instead of push_kv /
+ * push_lmdb — HB_EUNMATCHING_DISTANCE if the file was written for another distance, HB_EFORMAT if it is corrupt —
+ * and hb_index_finalize uploads it.  The file is a cache: the caller keys it (environment, index, the LMDB
+ * transaction id reported by hb_lmdb_scan) and drops it when the index is rebuilt.  No reference counterpart. */
+hb_status hb_index_save(const hb_index*, const char* path);
+hb_status hb_index_load(hb_index*, const char* path);
+
 /* Route (b): flat arrays (bench / tests).  ids ascending & unique; rows = n x dims f32 (float
  * metrics) or n x ceil(dims/64) u64 code words (binary metrics); hdr = n header norms (Cosine,
  * BQ-Cosine) or NULL; per layer l: offsets[l] has n+1 u64 entries, nbrs[l] holds neighbour ITEM IDS,
@@ -114,18 +123,40 @@ int hb_index_contains_item(const hb_index*, uint32_t item);
 hb_status hb_index_item_vector(const hb_index*, uint32_t item, float* out);
 
 /* ---- QueryBuilder (src/reader.rs:60-261) ------------------------------------------------------ */
+struct hb_cancel_token;
 typedef struct {
     const uint32_t* candidates; /* QueryBuilder::candidates (reader.rs:200-203): item ids, any order; NULL = none */
     uint64_t n_candidates;
     int has_candidates;         /* distinguishes "no bitmap" from "empty bitmap" */
     uint32_t linear_below;      /* QueryBuilder::linear_below, default 1000 (reader.rs:29,234-237) */
     float linear_below_ratio;   /* QueryBuilder::linear_below_ratio, default 1.0 (reader.rs:32,252-260) */
+    /* by_vector_with_cancellation / by_item_with_cancellation (reader.rs:91-188): the `cancel_fn` closure cannot cross
+     * the ABI; its two practical shapes can.  `cancel` = a token another host thread trips (hb_cancel_token_cancel —
+     * what `|| Instant::now() > deadline` or an abort flag amount to); the kernels poll it where the reference calls
+     * cancel_fn (before every layer-0 pop, reader.rs:330; once per 32 candidates of a linear scan, reader.rs:684).
+     * `cancel_after_polls` = the deterministic closure "true from its N-th call on" (0 = never), polled exactly like
+     * the reference polls cancel_fn — used to test parity of the Cancelled(..) results.  Both NULL/0: by_vector. */
+    const struct hb_cancel_token* cancel;
+    uint64_t cancel_after_polls;
 } hb_query_opts;
+
+/* A cancellation flag resident on `device`.  cancel / reset / is_cancelled may be called from any host thread while
+ * searches that carry the token are running. */
+typedef struct hb_cancel_token hb_cancel_token;
+hb_status hb_cancel_token_create(int device, hb_cancel_token** out);
+hb_status hb_cancel_token_cancel(hb_cancel_token*);
+hb_status hb_cancel_token_reset(hb_cancel_token*);
+int hb_cancel_token_is_cancelled(const hb_cancel_token*);
+void hb_cancel_token_free(hb_cancel_token*);
 
 /* per-query counters written by the search kernels (u64 each) */
 enum { HB_CTR_DIST_UPPER = 0, HB_CTR_DIST_L0 = 1, HB_CTR_EXP_UPPER = 2, HB_CTR_EXP_L0 = 3,
        HB_CTR_DEG_UPPER = 4, HB_CTR_DEG_L0 = 5, HB_CTR_FLAGS = 6, HB_CTR_RESERVED = 7, HB_N_CTR = 8 };
-enum { HB_FLAG_FALLBACK = 1, HB_FLAG_LINEAR = 2, HB_FLAG_SLOW_PATH = 4 };
+enum { HB_FLAG_FALLBACK = 1, HB_FLAG_LINEAR = 2, HB_FLAG_SLOW_PATH = 4, HB_FLAG_CANCELLED = 8 };
+/* Searched::did_cancel (reader.rs:36-57): bit 31 of out_len[i] when the query was cancelled (only possible when the
+ * call passed a cancel token or cancel_after_polls); the low 31 bits stay the number of results. */
+#define HB_LEN_CANCELLED 0x80000000u
+#define HB_LEN_NONE 0xFFFFFFFFu
 
 /* reader.nns(count).ef_search(..).by_vector(..) for a batch of nq queries (reader.rs:132-148 ->
  * 642-665 -> 722-800).  `count` = nns(count); `ef` = the QueryBuilder.ef field as the reference

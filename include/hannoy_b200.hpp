@@ -61,13 +61,29 @@ inline const char* name() { return hb_metric_name(D::metric); }
 // ---- src/reader.rs:36-57 ---------------------------------------------------------------------------------
 struct Searched {
     std::vector<std::pair<ItemId, float>> nns;
-    bool did_cancel_ = false;  // cancellation closures do not cross the ABI: always false
+    bool did_cancel_ = false;  // set when the query carried a CancelToken / poll budget and was interrupted
     bool did_cancel() const { return did_cancel_; }
     std::vector<std::pair<ItemId, float>> into_nns() && { return std::move(nns); }
 };
 
 template <class D>
 class Reader;
+
+// What a `cancel_fn` closure (reader.rs:108-118,167-188) becomes on this side of the ABI: a flag on the device that any
+// host thread may trip while searches carrying it are in flight.
+class CancelToken {
+  public:
+    explicit CancelToken(int device = 0) { check(hb_cancel_token_create(device, &t_)); }
+    CancelToken(const CancelToken&) = delete;
+    ~CancelToken() { hb_cancel_token_free(t_); }
+    void cancel() { check(hb_cancel_token_cancel(t_)); }
+    void reset() { check(hb_cancel_token_reset(t_)); }
+    bool is_cancelled() const { return hb_cancel_token_is_cancelled(t_) != 0; }
+    const hb_cancel_token* raw() const { return t_; }
+
+  private:
+    hb_cancel_token* t_ = nullptr;
+};
 
 // ---- src/reader.rs:60-261 ----------------------------------------------------------------------------------
 template <class D>
@@ -77,6 +93,10 @@ class QueryBuilder {
     QueryBuilder& candidates(const std::vector<ItemId>& c) { cand_ = &c; return *this; }
     QueryBuilder& linear_below(size_t threshold) { linear_below_ = threshold; return *this; }
     QueryBuilder& linear_below_ratio(float ratio) { linear_below_ratio_ = ratio; return *this; }
+    // *_with_cancellation: the searches of this builder poll `token` where the reference polls cancel_fn (reader.rs:330,684)
+    QueryBuilder& with_cancellation(const CancelToken& token) { cancel_ = token.raw(); return *this; }
+    // the deterministic closure "true from its n-th call on" (0 = never)
+    QueryBuilder& cancel_after_polls(uint64_t n) { cancel_after_ = n; return *this; }
 
     // nq x dimensions row-major; one kernel launch for the whole batch
     std::vector<Searched> by_vectors(const float* q, size_t nq, size_t dims) const {
@@ -97,7 +117,7 @@ class QueryBuilder {
                                 o.dist.data(), o.len.data(), nullptr));
         std::vector<std::optional<Searched>> res(items.size());
         for (size_t i = 0; i < items.size(); ++i)
-            if (o.len[i] != UINT32_MAX) res[i] = o.get(i, count_);  // reader.rs:826: None if the item is absent
+            if (o.len[i] != HB_LEN_NONE) res[i] = o.get(i, count_);  // reader.rs:826: None if the item is absent
         return res;
     }
     std::optional<Searched> by_item(ItemId item) const { return std::move(by_items({item})[0]); }
@@ -110,7 +130,8 @@ class QueryBuilder {
         Out(size_t nq, size_t k) : ids(nq * k), len(nq), dist(nq * k) {}
         Searched get(size_t i, size_t k) const {
             Searched s;
-            for (uint32_t j = 0; j < len[i]; ++j) s.nns.emplace_back(ids[i * k + j], dist[i * k + j]);
+            s.did_cancel_ = (len[i] & HB_LEN_CANCELLED) != 0;
+            for (uint32_t j = 0; j < (len[i] & ~HB_LEN_CANCELLED); ++j) s.nns.emplace_back(ids[i * k + j], dist[i * k + j]);
             return s;
         }
     };
@@ -122,6 +143,8 @@ class QueryBuilder {
         o.has_candidates = cand_ != nullptr;
         o.linear_below = (uint32_t)linear_below_;
         o.linear_below_ratio = linear_below_ratio_;
+        o.cancel = cancel_;
+        o.cancel_after_polls = cancel_after_;
         return o;
     }
     const Reader<D>* reader_;
@@ -130,6 +153,8 @@ class QueryBuilder {
     size_t ef_ = 100;               // DEFAULT_EF_SEARCH, reader.rs:23
     size_t linear_below_ = 1000;    // reader.rs:29
     float linear_below_ratio_ = 1.0f;  // reader.rs:32
+    const hb_cancel_token* cancel_ = nullptr;
+    uint64_t cancel_after_ = 0;
 };
 
 // ---- src/reader.rs:374-431,545-620 ---------------------------------------------------------------------------
@@ -145,6 +170,13 @@ class Reader {
         for (const auto& [k, v] : kv)
             check(hb_index_push_kv(r.ix_, (const uint8_t*)k.data(), k.size(), (const uint8_t*)v.data(), v.size()));
         check(hb_index_finalize(r.ix_, device));
+        return r;
+    }
+    // Reader::open from the LMDB environment on disk (directory holding data.mdb, or the data file itself); db_name =
+    // nullptr for the unnamed database.  The library walks the B+tree itself: no liblmdb, no transaction object.
+    static Reader open_path(const char* path, const char* db_name, uint16_t index, int device = 0) {
+        Reader r;
+        check(hb_index_open_lmdb(path, db_name, D::metric, index, device, &r.ix_));
         return r;
     }
     Reader(Reader&& o) noexcept : ix_(o.ix_) { o.ix_ = nullptr; }

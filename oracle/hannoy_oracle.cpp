@@ -472,7 +472,15 @@ struct Db {
 struct Counters {  // per query
     uint64_t dist_upper = 0, dist_l0 = 0, exp_upper = 0, exp_l0 = 0, deg_upper = 0, deg_l0 = 0, flags = 0, pad = 0;
 };
-enum : uint64_t { FLAG_FALLBACK = 1, FLAG_LINEAR = 2 };
+enum : uint64_t { FLAG_FALLBACK = 1, FLAG_LINEAR = 2, FLAG_CANCELLED = 8 };
+
+// A deterministic `cancel_fn: impl Fn() -> bool` (reader.rs:112,171): true from its `after`-th call on (1-based);
+// after == 0 never cancels (what by_vector / by_item pass, reader.rs:143).  One instance per query: the closure is
+// shared by every visit of that query (reader.rs:731,817).
+struct Cancel {
+    uint64_t after = 0, calls = 0;
+    bool operator()() { ++calls; return after != 0 && calls >= after; }
+};
 
 struct Scratch {
     std::vector<uint32_t> epoch;  // visited set (`path: RoaringBitmap`, reader.rs:734), exact
@@ -504,9 +512,10 @@ struct ResHeap {
 
 // Visitor::visit — src/reader.rs:301-369.  `cand` = optional candidates filter over slots,
 // `excl` = slot removed from the candidates (nns_by_item, reader.rs:839-840) or UINT32_MAX.
-static void visit(const Db& db, const Query& q, const std::vector<uint32_t>& eps, uint32_t level, size_t ef,
+// Returns true for Completion::Cancelled(res).  cancel == nullptr is the `&|| false` of the descent (reader.rs:736).
+static bool visit(const Db& db, const Query& q, const std::vector<uint32_t>& eps, uint32_t level, size_t ef,
                   const std::vector<uint8_t>* cand, bool filter_all_but, uint32_t excl, Scratch& path,
-                  ResHeap& res, Counters& ctr) {
+                  ResHeap& res, Counters& ctr, Cancel* cancel = nullptr) {
     auto passes = [&](uint32_t s) {
         if (cand) return (*cand)[s] != 0 && s != excl;
         if (filter_all_but) return s != excl;
@@ -529,6 +538,7 @@ static void visit(const Db& db, const Query& q, const std::vector<uint32_t>& eps
         if (passes(ep)) res.push({f2u(dist), ep});
     }
     while (!search_queue.empty()) {  // reader.rs:329-367
+        if (cancel && (*cancel)()) return true;  // reader.rs:330-332
         float f = u2f(search_queue.top().first);
         float f_max = res.len() ? u2f(res.peek_max().first) : 3.40282347e+38f;
         if (f > f_max) break;
@@ -549,6 +559,7 @@ static void visit(const Db& db, const Query& q, const std::vector<uint32_t>& eps
             }
         }
     }
+    return false;
 }
 
 // drain_asc().take(count)
@@ -566,6 +577,7 @@ struct Opts {
     size_t linear_below = 1000;
     float linear_below_ratio = 1.0f;
     size_t cand_in_db = 0;
+    uint64_t cancel_after = 0;  // see Cancel
 };
 
 // should_linear_scan — reader.rs:622-640
@@ -576,9 +588,10 @@ static bool should_linear_scan(const Db& db, const Opts& o) {
     return below_threshold && below_ratio;
 }
 // brute_force_search — reader.rs:668-711
-static void brute_force(const Db& db, const Query& q, const Opts& o, uint32_t* out_ids, float* out_dist, uint32_t* out_len, Counters& ctr) {
+static void brute_force(const Db& db, const Query& q, const Opts& o, uint32_t* out_ids, float* out_dist, uint32_t* out_len, Counters& ctr, Cancel& cancel) {
     std::vector<Scored> heap;  // BinaryHeap<(OrderedFloat, ItemId)> max-heap
     for (uint32_t id : *o.cand_ids) {
+        if (cancel()) { ctr.flags |= FLAG_CANCELLED; break; }  // reader.rs:684-687
         int64_t s = db.slot_of(id);
         if (s < 0) continue;
         float d = distance(db.metric, db.dims, db.row(s), db.hdr[s], q.row, q.hdr);  // D::distance(&item, query)
@@ -599,7 +612,9 @@ static void brute_force(const Db& db, const Query& q, const Opts& o, uint32_t* o
 }
 
 // hnsw_search — reader.rs:722-800
-static void hnsw_search(const Db& db, const Query& q, const Opts& o, Scratch& path, uint32_t* out_ids, float* out_dist, uint32_t* out_len, Counters& ctr) {
+static void hnsw_search(const Db& db, const Query& q, const Opts& o, Scratch& path, uint32_t* out_ids, float* out_dist, uint32_t* out_len, Counters& ctr, Cancel& cancel) {
+    // return_if_cancelled! (reader.rs:749-764): only the interrupted visit's heap is returned
+    auto cancelled = [&](ResHeap& r) { ctr.flags |= FLAG_CANCELLED; std::vector<Scored> f = r.h; drain_asc_take(db, f, o.count, out_ids, out_dist, out_len); };
     std::vector<uint32_t> eps = db.entry_points;
     ResHeap res;
     path.reset(db.n());
@@ -609,7 +624,7 @@ static void hnsw_search(const Db& db, const Query& q, const Opts& o, Scratch& pa
     }
     path.reset(db.n());  // path.clear()
     size_t ef = std::max(o.ef, o.count);
-    visit(db, q, eps, 0, ef, o.cand, false, UINT32_MAX, path, res, ctr);
+    if (visit(db, q, eps, 0, ef, o.cand, false, UINT32_MAX, path, res, ctr, &cancel)) { cancelled(res); return; }
     std::vector<Scored> neighbours = res.h;
     if (neighbours.size() < o.count) {  // reader.rs:771-795
         ctr.flags |= FLAG_FALLBACK;
@@ -617,7 +632,7 @@ static void hnsw_search(const Db& db, const Query& q, const Opts& o, Scratch& pa
             if (path.contains(s)) continue;
             eps.assign(1, s);
             size_t ef2 = o.ef > neighbours.size() ? o.ef - neighbours.size() : 0;  // saturating_sub
-            visit(db, q, eps, 0, ef2, o.cand, false, UINT32_MAX, path, res, ctr);
+            if (visit(db, q, eps, 0, ef2, o.cand, false, UINT32_MAX, path, res, ctr, &cancel)) { cancelled(res); return; }
             neighbours.insert(neighbours.end(), res.h.begin(), res.h.end());
             if (neighbours.size() >= o.ef) break;
         }
@@ -628,9 +643,10 @@ static void hnsw_search(const Db& db, const Query& q, const Opts& o, Scratch& pa
 // nns_by_vec — reader.rs:642-665
 static void nns_by_vec(const Db& db, const Query& q, const Opts& o, Scratch& path, uint32_t* out_ids, float* out_dist, uint32_t* out_len, Counters& ctr) {
     *out_len = 0;
+    Cancel cancel{o.cancel_after};
     if (db.n() == 0 || (o.cand_ids && o.cand_in_db == 0)) return;
-    if (o.cand_ids && should_linear_scan(db, o)) { brute_force(db, q, o, out_ids, out_dist, out_len, ctr); return; }
-    hnsw_search(db, q, o, path, out_ids, out_dist, out_len, ctr);
+    if (o.cand_ids && should_linear_scan(db, o)) { brute_force(db, q, o, out_ids, out_dist, out_len, ctr, cancel); return; }
+    hnsw_search(db, q, o, path, out_ids, out_dist, out_len, ctr, cancel);
 }
 
 // nns_by_item — reader.rs:809-894.  Returns false for `None`.
@@ -640,12 +656,14 @@ static bool nns_by_item(const Db& db, uint32_t item, const Opts& o, Scratch& pat
     int64_t is = db.slot_of(item);
     if (is < 0) return false;
     Query q{db.row(is), new_header(db.metric, db.dims, db.row(is))};
-    if (o.cand_ids && should_linear_scan(db, o)) { brute_force(db, q, o, out_ids, out_dist, out_len, ctr); return true; }
+    Cancel cancel{o.cancel_after};
+    if (o.cand_ids && should_linear_scan(db, o)) { brute_force(db, q, o, out_ids, out_dist, out_len, ctr, cancel); return true; }
     size_t ef = std::max(o.ef, o.count);
     path.reset(db.n());
     std::vector<uint32_t> eps(1, (uint32_t)is);
     ResHeap res;
-    visit(db, q, eps, 0, ef, o.cand, true, (uint32_t)is, path, res, ctr);
+    auto cancelled = [&](ResHeap& r) { ctr.flags |= FLAG_CANCELLED; std::vector<Scored> f = r.h; drain_asc_take(db, f, o.count, out_ids, out_dist, out_len); };
+    if (visit(db, q, eps, 0, ef, o.cand, true, (uint32_t)is, path, res, ctr, &cancel)) { cancelled(res); return true; }
     std::vector<Scored> neighbours = res.h;
     if (neighbours.size() < o.count) {  // reader.rs:865-889
         ctr.flags |= FLAG_FALLBACK;
@@ -653,7 +671,7 @@ static bool nns_by_item(const Db& db, uint32_t item, const Opts& o, Scratch& pat
             if (path.contains(s)) continue;
             eps.assign(1, s);
             size_t ef2 = o.count - neighbours.size();
-            visit(db, q, eps, 0, ef2, o.cand, true, (uint32_t)is, path, res, ctr);
+            if (visit(db, q, eps, 0, ef2, o.cand, true, (uint32_t)is, path, res, ctr, &cancel)) { cancelled(res); return true; }
             neighbours.insert(neighbours.end(), res.h.begin(), res.h.end());
             if (neighbours.size() >= o.count) break;
         }
@@ -1014,12 +1032,17 @@ extern "C" {
 // reader.nns(count).ef_search(..).candidates(..).linear_below(..).by_vector(q) for a batch.
 // `ef` is the raw QueryBuilder.ef field.  cand==NULL <=> no candidates bitmap.
 // out_ids/out_dist: nq*count, out_len: nq, counters: nq*8 u64 (nullable)
+static thread_local uint64_t g_cancel_after = 0;
+// the next orc_search_* call of this thread runs with `cancel_fn` = "true from the after-th call on" (0 = never); the
+// FLAG_CANCELLED bit of the counters' flags word reports Completion::Cancelled per query
+void orc_set_cancel_after(uint64_t after) { g_cancel_after = after; }
 int orc_search_by_vector(void* h, const float* q, uint64_t nq, uint32_t count, uint32_t ef, const uint32_t* cand, uint64_t n_cand,
                          int has_cand, uint32_t linear_below, float linear_ratio, uint32_t* out_ids, float* out_dist, uint32_t* out_len,
                          uint64_t* counters, int n_threads) {
     Db& db = *(Db*)h; prep(db);
     CandPrep cp;
     Opts o; o.count = count; o.ef = ef; o.linear_below = linear_below; o.linear_below_ratio = linear_ratio;
+    o.cancel_after = g_cancel_after; g_cancel_after = 0;
     if (has_cand) { prep_cand(db, cand, n_cand, cp); o.cand = &cp.dense; o.cand_ids = &cp.ids; o.cand_in_db = cp.in_db; }
     size_t nw = n_words(db.dims);
     par_for(nq, n_threads, [&](uint64_t i, Scratch& sc) {
@@ -1045,6 +1068,7 @@ int orc_search_by_item(void* h, const uint32_t* items, uint64_t nq, uint32_t cou
     Db& db = *(Db*)h; prep(db);
     CandPrep cp;
     Opts o; o.count = count; o.ef = ef; o.linear_below = linear_below; o.linear_below_ratio = linear_ratio;
+    o.cancel_after = g_cancel_after; g_cancel_after = 0;
     if (has_cand) { prep_cand(db, cand, n_cand, cp); o.cand = &cp.dense; o.cand_ids = &cp.ids; o.cand_in_db = cp.in_db; }
     par_for(nq, n_threads, [&](uint64_t i, Scratch& sc) {
         Counters c;

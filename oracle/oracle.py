@@ -16,7 +16,7 @@ METRICS = {
     "euclidean": 0, "cosine": 1, "manhattan": 2, "hamming": 3,
     "binary quantized cosine": 4, "binary quantized euclidean": 5, "binary quantized manhattan": 6,
 }
-FLAG_FALLBACK, FLAG_LINEAR = 1, 2
+FLAG_FALLBACK, FLAG_LINEAR, FLAG_CANCELLED = 1, 2, 8
 
 
 def build(force=False):
@@ -50,7 +50,7 @@ def lib():
             "orc_db_layer_nnz": (u64, [vp, u32]), "orc_db_get_layer": (None, [vp, u32, vp, vp]),
             "orc_search_by_vector": (i32, [vp, vp, u64, u32, u32, vp, u64, i32, u32, f32, vp, vp, vp, vp, i32]),
             "orc_search_by_item": (i32, [vp, vp, u64, u32, u32, vp, u64, i32, u32, f32, vp, vp, vp, vp, i32]),
-            "orc_exact_knn": (i32, [vp, vp, u64, u32, vp, vp, i32]),
+            "orc_exact_knn": (i32, [vp, vp, u64, u32, vp, vp, i32]), "orc_set_cancel_after": (None, [u64]),
             "orc_dot_product": (f32, [vp, vp, u64]), "orc_euclidean": (f32, [vp, vp, u64]),
             "orc_dot_scalar": (f32, [vp, vp, u64]), "orc_euclid_scalar": (f32, [vp, vp, u64]),
             "orc_dot_sse": (f32, [vp, vp, u64]), "orc_euclid_sse": (f32, [vp, vp, u64]),
@@ -170,7 +170,8 @@ class OracleDb:
             res.append((off, nbr))
         return res
 
-    def _search(self, fn, qarr, nq, count, ef, candidates, linear_below, linear_below_ratio, n_threads, counters):
+    def _search(self, fn, qarr, nq, count, ef, candidates, linear_below, linear_below_ratio, n_threads, counters, cancel_after=0):
+        lib().orc_set_cancel_after(cancel_after)  # cancel_fn = "true from its cancel_after-th call on" (0 = never)
         ids = np.zeros((nq, count), np.uint32)
         dist = np.zeros((nq, count), np.float32)
         lens = np.zeros(nq, np.uint32)
@@ -181,19 +182,19 @@ class OracleDb:
         return ids, dist, lens, ctr
 
     def search_by_vector(self, q, count, ef=100, candidates=None, linear_below=1000, linear_below_ratio=1.0,
-                         n_threads=1, counters=False):
+                         n_threads=1, counters=False, cancel_after=0):
         """reader.nns(count)[.ef_search()].by_vector for each row of q. `ef` is the raw
         QueryBuilder.ef field (callers apply ef_search's max(ef, count) themselves)."""
         q = _f32(q).reshape(-1, self.dims)
         return self._search(lib().orc_search_by_vector, q, len(q), count, ef, candidates, linear_below,
-                            linear_below_ratio, n_threads, counters)
+                            linear_below_ratio, n_threads, counters, cancel_after)
 
     def search_by_item(self, items, count, ef=100, candidates=None, linear_below=1000, linear_below_ratio=1.0,
-                       n_threads=1, counters=False):
+                       n_threads=1, counters=False, cancel_after=0):
         """by_item for each id; lens == 0xFFFFFFFF encodes `None`."""
         items = _u32(items)
         return self._search(lib().orc_search_by_item, items, len(items), count, ef, candidates, linear_below,
-                            linear_below_ratio, n_threads, counters)
+                            linear_below_ratio, n_threads, counters, cancel_after)
 
     def exact_knn(self, q, k, n_threads=1):
         q = _f32(q).reshape(-1, self.dims)

@@ -17,19 +17,33 @@ pub const HB_ENEED_BUILD: hb_status = 9;
 pub type hb_metric = c_int; // 0 euclidean .. 6 binary quantized manhattan, see hb_metric_from_name
 
 #[repr(C)]
+pub struct hb_cancel_token {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
 pub struct hb_query_opts {
     pub candidates: *const u32,
     pub n_candidates: u64,
     pub has_candidates: c_int,
     pub linear_below: u32,
     pub linear_below_ratio: f32,
+    pub cancel: *const hb_cancel_token,
+    pub cancel_after_polls: u64,
 }
+pub const HB_LEN_CANCELLED: u32 = 0x8000_0000;
 
 extern "C" {
     pub fn hb_metric_from_name(name: *const c_char) -> c_int;
     pub fn hb_index_begin(m: hb_metric, index: u16, out: *mut *mut hb_index) -> hb_status;
     pub fn hb_index_push_kv(ix: *mut hb_index, key: *const u8, klen: usize, val: *const u8, vlen: usize) -> hb_status;
     pub fn hb_index_finalize(ix: *mut hb_index, device: c_int) -> hb_status;
+    pub fn hb_index_open_lmdb(
+        path: *const c_char, db_name: *const c_char, m: hb_metric, index: u16, device: c_int, out: *mut *mut hb_index,
+    ) -> hb_status;
+    pub fn hb_cancel_token_create(device: c_int, out: *mut *mut hb_cancel_token) -> hb_status;
+    pub fn hb_cancel_token_cancel(t: *mut hb_cancel_token) -> hb_status;
+    pub fn hb_cancel_token_free(t: *mut hb_cancel_token);
     pub fn hb_index_free(ix: *mut hb_index);
     pub fn hb_index_dimensions(ix: *const hb_index) -> u32;
     pub fn hb_index_n_items(ix: *const hb_index) -> u64;

@@ -43,6 +43,7 @@ fn check(st: ffi::hb_status, dims: (usize, usize)) -> Result<()> {
 pub struct GpuReader<D: Distance> {
     raw: *mut ffi::hb_index,
     dimensions: usize,
+    device: i32,
     _marker: PhantomData<D>,
 }
 
@@ -65,7 +66,7 @@ impl<D: Distance> GpuReader<D> {
         assert!(metric >= 0, "distance {:?} has no GPU kernel", D::name());
         let mut raw = std::ptr::null_mut();
         check(unsafe { ffi::hb_index_begin(metric, index, &mut raw) }, (0, 0))?;
-        let this = GpuReader { raw, dimensions: 0, _marker: PhantomData };
+        let this = GpuReader { raw, dimensions: 0, device, _marker: PhantomData };
         // every key of this index starts with its big-endian u16 (key.rs:54-66)
         let prefix = index.to_be_bytes();
         let raw_db = database.remap_types::<Bytes, Bytes>();
@@ -81,6 +82,25 @@ impl<D: Distance> GpuReader<D> {
         }
         let dimensions = unsafe { ffi::hb_index_dimensions(this.raw) } as usize;
         Ok(GpuReader { dimensions, ..this })
+    }
+
+    /// `Reader::open` without heed: the library walks `<path>/data.mdb` itself (`db_name = None` is the unnamed
+    /// database), for processes that do not hold the LMDB environment open.
+    pub fn open_path(path: &std::path::Path, db_name: Option<&str>, index: u16, device: i32) -> Result<Self> {
+        let name = CString::new(D::name()).unwrap();
+        let metric = unsafe { ffi::hb_metric_from_name(name.as_ptr()) };
+        let cpath = CString::new(path.to_string_lossy().as_bytes()).unwrap();
+        let cdb = db_name.map(|n| CString::new(n).unwrap());
+        let mut raw = std::ptr::null_mut();
+        let st = unsafe {
+            ffi::hb_index_open_lmdb(cpath.as_ptr(), cdb.as_ref().map_or(std::ptr::null(), |c| c.as_ptr()), metric, index, device, &mut raw)
+        };
+        match st {
+            ffi::HB_EUNMATCHING_DISTANCE => return Err(Error::UnmatchingDistance { expected: last_error(), received: D::name() }),
+            st => check(st, (0, 0))?,
+        }
+        let dimensions = unsafe { ffi::hb_index_dimensions(raw) } as usize;
+        Ok(GpuReader { raw, dimensions, device, _marker: PhantomData })
     }
 
     pub fn dimensions(&self) -> usize {
@@ -115,6 +135,7 @@ impl<D: Distance> GpuReader<D> {
             ef: DEFAULT_EF_SEARCH,
             linear_below: DEFAULT_LINEAR_SCAN_THRESHOLD,
             linear_below_ratio: DEFAULT_LINEAR_SCAN_THRESHOLD_RATIO,
+            cancel: std::ptr::null(),
         }
     }
 }
@@ -127,6 +148,36 @@ pub struct GpuQueryBuilder<'a, D: Distance> {
     ef: usize,
     linear_below: usize,
     linear_below_ratio: f32,
+    cancel: *const ffi::hb_cancel_token,
+}
+
+/// Runs `search` while a watcher thread evaluates `cancel_fn` on the host and trips a device-side token the first time
+/// it returns true: the kernels poll that token where the reference calls `cancel_fn` (reader.rs:330,684).
+fn with_watcher<T>(device: i32, cancel_fn: impl Fn() -> bool + Sync, search: impl FnOnce(*const ffi::hb_cancel_token) -> Result<T>) -> Result<T> {
+    use std::sync::atomic::{AtomicBool, Ordering};
+    let mut tok = std::ptr::null_mut();
+    check(unsafe { ffi::hb_cancel_token_create(device, &mut tok) }, (0, 0))?;
+    struct SendPtr(*mut ffi::hb_cancel_token);
+    unsafe impl Send for SendPtr {}
+    unsafe impl Sync for SendPtr {}
+    let tokp = SendPtr(tok);
+    let done = AtomicBool::new(false);
+    let res = std::thread::scope(|s| {
+        s.spawn(|| {
+            while !done.load(Ordering::Acquire) {
+                if cancel_fn() {
+                    unsafe { ffi::hb_cancel_token_cancel(tokp.0) };
+                    break;
+                }
+                std::thread::sleep(std::time::Duration::from_micros(50));
+            }
+        });
+        let r = search(tok as *const _);
+        done.store(true, Ordering::Release);
+        r
+    });
+    unsafe { ffi::hb_cancel_token_free(tok) };
+    res
 }
 
 impl<'a, D: Distance> GpuQueryBuilder<'a, D> {
@@ -154,17 +205,35 @@ impl<'a, D: Distance> GpuQueryBuilder<'a, D> {
             has_candidates: self.candidates.is_some() as i32,
             linear_below: self.linear_below.min(u32::MAX as usize) as u32,
             linear_below_ratio: self.linear_below_ratio,
+            cancel: self.cancel,
+            cancel_after_polls: 0,
         }
+    }
+
+    /// `QueryBuilder::by_vector_with_cancellation` (reader.rs:167-188)
+    pub fn by_vector_with_cancellation(&self, rtxn: &RoTxn, vector: &'a [f32], cancel_fn: impl Fn() -> bool + Sync) -> Result<Searched> {
+        with_watcher(self.reader.device, cancel_fn, |tok| {
+            let qb = GpuQueryBuilder { cancel: tok, ..*self };
+            qb.by_vector(rtxn, vector)
+        })
+    }
+
+    /// `QueryBuilder::by_item_with_cancellation` (reader.rs:108-118)
+    pub fn by_item_with_cancellation(&self, rtxn: &RoTxn, item: ItemId, cancel_fn: impl Fn() -> bool + Sync) -> Result<Option<Searched>> {
+        with_watcher(self.reader.device, cancel_fn, |tok| {
+            let qb = GpuQueryBuilder { cancel: tok, ..*self };
+            qb.by_item(rtxn, item)
+        })
     }
 
     fn unpack(&self, nq: usize, ids: Vec<u32>, dist: Vec<f32>, lens: Vec<u32>) -> Vec<Option<Searched>> {
         (0..nq)
             .map(|i| {
                 (lens[i] != u32::MAX).then(|| {
-                    let n = lens[i] as usize;
+                    let n = (lens[i] & !ffi::HB_LEN_CANCELLED) as usize;
                     let row = i * self.count;
                     let nns = (0..n).map(|j| (ids[row + j], dist[row + j])).collect();
-                    Searched { nns, did_cancel: false }
+                    Searched { nns, did_cancel: lens[i] & ffi::HB_LEN_CANCELLED != 0 }
                 })
             })
             .collect()

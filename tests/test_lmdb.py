@@ -231,3 +231,81 @@ def test_open_path_search_equals_oracle(tmp_path, metric, dims, named):
         assert np.array_equal(got[3][:, :6], want[3][:, :6])
     items = np.array([ids[0], ids[17], ids[-1], ids[-1] + 1], np.uint32)
     assert_same(rd.nns(5).by_items_raw(items), db.search_by_item(items, 5, ef=100), "lmdb route by_item")
+
+
+# ---- flat-file snapshot cache ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric,dims", [("cosine", 100), ("hamming", 130), ("binary quantized euclidean", 64)])
+def test_snapshot_file_roundtrip_on_the_host(tmp_path, metric, dims):
+    """hb_index_save after the host half of finalize, hb_index_load into a fresh index: same ids / vectors / entry points /
+    version; corrupt, truncated, foreign-distance and foreign-index files are refused."""
+    n = 500
+    ids = np.sort(np.random.default_rng(1).choice(1 << 24, n, replace=False)).astype(np.uint32)
+    db, x = make_db(metric, n, dims, seed=4, ids=ids)
+    lib = L.lib()
+    mid = hb.reader._distance_of(metric).ID
+    h = C.c_void_p()
+    assert lib.hb_index_begin(mid, 2, C.byref(h)) == L.HB_OK
+    fn = os.fsencode(str(tmp_path / "snap.hb"))
+    for k, v in db.export_kv(2):
+        assert lib.hb_index_push_kv(h, bytes(k), len(k), bytes(v), len(v)) == L.HB_OK
+    assert lib.hb_index_save(h, fn) == L.HB_ESTATE                 # nothing decoded yet
+    assert lib.hb_index_finalize(h, 0) in (L.HB_OK, L.HB_ECUDA)    # the host half runs either way
+    assert lib.hb_index_save(h, fn) == L.HB_OK, lib.hb_last_error()
+    g = C.c_void_p()
+    assert lib.hb_index_begin(mid, 2, C.byref(g)) == L.HB_OK
+    assert lib.hb_index_load(g, fn) == L.HB_OK, lib.hb_last_error()
+    assert lib.hb_index_load(g, fn) == L.HB_ESTATE                 # not empty any more
+    assert lib.hb_index_finalize(g, 0) in (L.HB_OK, L.HB_ECUDA)
+    for a in ("hb_index_n_items", "hb_index_dimensions", "hb_index_max_level", "hb_index_n_entry_points"):
+        assert getattr(lib, a)(g) == getattr(lib, a)(h), a
+    ga, ha = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+    lib.hb_index_item_ids(g, ga.ctypes.data_as(C.c_void_p), n)
+    lib.hb_index_item_ids(h, ha.ctypes.data_as(C.c_void_p), n)
+    assert np.array_equal(ga, ha) and np.array_equal(ga, ids)
+    va, vb = np.zeros(dims, np.float32), np.zeros(dims, np.float32)
+    for s in range(0, n, 37):
+        assert lib.hb_index_item_vector(g, int(ids[s]), va.ctypes.data_as(C.c_void_p)) == L.HB_OK
+        assert lib.hb_index_item_vector(h, int(ids[s]), vb.ctypes.data_as(C.c_void_p)) == L.HB_OK
+        assert np.array_equal(va, vb)
+    ver = [C.c_uint32() for _ in range(3)]
+    assert lib.hb_index_version(g, *[C.byref(v) for v in ver]) == L.HB_OK and [v.value for v in ver] == [0, 1, 3]
+    # saving the loaded index reproduces the file byte for byte
+    fn2 = os.fsencode(str(tmp_path / "snap2.hb"))
+    assert lib.hb_index_save(g, fn2) == L.HB_OK
+    blob = open(fn, "rb").read()
+    assert open(fn2, "rb").read() == blob
+    lib.hb_index_free(g)
+    lib.hb_index_free(h)
+
+    def load(blob_, metric_id=mid, index=2):
+        p = str(tmp_path / "x.hb")
+        open(p, "wb").write(blob_)
+        t = C.c_void_p()
+        assert lib.hb_index_begin(metric_id, index, C.byref(t)) == L.HB_OK
+        st = lib.hb_index_load(t, os.fsencode(p))
+        lib.hb_index_free(t)
+        return st
+    assert load(blob) == L.HB_OK
+    assert load(blob[:-9]) == L.HB_EFORMAT                                  # truncated
+    flipped = bytearray(blob); flipped[len(blob) // 2] ^= 0x40
+    assert load(bytes(flipped)) == L.HB_EFORMAT                             # checksum
+    assert load(b"not a snapshot at all") == L.HB_EFORMAT
+    assert load(blob, metric_id=(mid + 1) % 7) == L.HB_EUNMATCHING_DISTANCE
+    assert load(blob, index=3) == L.HB_EINVAL
+
+
+@pytest.mark.gpu
+def test_snapshot_file_search_equals_oracle(tmp_path):
+    db, x = make_db("cosine", 3000, 96, seed=6, kind="clustered")
+    path = _write_env(tmp_path, {0: db})
+    rd = hb.Reader.open_path(path, 0, "cosine")
+    rd.save(str(tmp_path / "c.hb"))
+    rd2 = hb.Reader.load(str(tmp_path / "c.hb"), 0, hb.Cosine)
+    q = make_vectors(64, 96, seed=2, kind="clustered")
+    want = db.search_by_vector(q, 10, ef=80, counters=True)
+    for r in (rd, rd2):
+        got = r.nns(10).ef_search(80).by_vectors_raw(q, counters=True)
+        assert_same(got, want, "snapshot file")
+        assert np.array_equal(got[3][:, :6], want[3][:, :6])
+    with pytest.raises(hb.UnmatchingDistance):
+        hb.Reader.load(str(tmp_path / "c.hb"), 0, hb.Euclidean)
