@@ -30,7 +30,7 @@ WORKLOADS = {
     # name: metric, n, dims, nq, k, ef candidates, generator
     "c1": dict(metric="euclidean", n=10_000, dims=128, nq=1_000, k=10, efs=[64], gen="uniform", seed=1,
                desc="10k x 128 f32 Euclidean, M=16/M0=32, efC=100, 1k queries top-10 ef_search=64"),
-    "c2": dict(metric="euclidean", n=1_000_000, dims=128, nq=10_000, k=10, efs=[32, 64, 128, 256], gen="sift", seed=3,
+    "c2": dict(metric="euclidean", n=1_000_000, dims=128, nq=10_000, k=10, efs=[32, 64, 128, 256], gen="siftlike", seed=3,
                desc="SIFT-shaped 1M x 128 f32 Euclidean, 10k-query batch, top-10"),
     "c3": dict(metric="cosine", n=1_000_000, dims=768, nq=10_000, k=10, efs=[32, 64, 128, 256], gen="lowrank", seed=5,
                desc="1M x 768 f32 Cosine (text-embedding shaped), 10k-query batch, top-10"),
@@ -54,10 +54,15 @@ def gen_vectors(gen, n, dims, seed, device):
     gb.manual_seed(1234)  # basis / cluster centres shared by base vectors and queries
     if gen == "uniform":
         return (torch.rand((n, dims), generator=g, device=device) * 2 - 1).float()
-    if gen == "sift":  # non-negative, ||x|| ~ 512: 64-cluster mixture clipped to [0, 255], rounded
-        centers = torch.rand((64, dims), generator=gb, device=device) * 60 + 10
-        idx = torch.randint(0, 64, (n,), generator=g, device=device)
-        x = centers[idx] + 25 * torch.randn((n, dims), generator=g, device=device)
+    if gen == "siftlike":  # SIFT-shaped: non-negative integers in [0, 255], ||x|| ~ 512, ~25 % zeros, low intrinsic dimension
+        # (64 clusters in a 32-d latent space pushed through a random linear map, + small noise, clipped and rounded) --
+        # i.i.d. noise around 64 centres in 128-d is adversarial for any graph index (recall@10 0.75 at ef = 256)
+        r, nc = 32, 64
+        A = torch.randn((r, dims), generator=gb, device=device) / (r ** 0.5)
+        C = torch.randn((nc, r), generator=gb, device=device) * 1.5
+        idx = torch.randint(0, nc, (n,), generator=g, device=device)
+        z = C[idx] + torch.randn((n, r), generator=g, device=device)
+        x = 27.0 + 21.5 * (z @ A) + 5.7 * torch.randn((n, dims), generator=g, device=device)
         return x.clamp_(0, 255).round_().float()
     if gen == "lowrank":  # embedding-shaped: 256 clusters in a 32-d latent space + small isotropic noise, unit norm
         r, nc = 32, 256

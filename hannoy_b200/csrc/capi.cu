@@ -566,6 +566,8 @@ static hb_status search_host(const hb_index* ix, const float* q, const uint32_t*
     if (!out_len || (count && (!out_ids || !out_dist))) { set_error("null output buffer"); return HB_EINVAL; }
     auto none = [&](uint32_t v) {
         for (uint64_t i = 0; i < nq; ++i) out_len[i] = v;
+        if (out_ids && count) std::memset(out_ids, 0, nq * (size_t)count * 4);
+        if (out_dist && count) std::memset(out_dist, 0, nq * (size_t)count * 4);
         if (out_ctr) std::memset(out_ctr, 0, nq * HB_N_CTR * 8);
     };
     // reader.rs:654-656 / 822-824

@@ -416,7 +416,7 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
     const uint32_t* off = ix.off[level];
     const uint32_t* nbr = ix.nbr[level];
     const uint32_t* nbrx = level == 0 ? ix.nbr0x : nullptr;
-    const bool defer = nbrx && c.p.pass == 0 && c.p.defer;
+    const bool defer = nbrx && c.p.pass == 0 && c.p.defer && !linear;  // a linear scan pops nothing (reader.rs:683-705)
     uint32_t spec_cs = 0xffffffffu, spec_adj = 0xffffffffu;  // adjacency line requested ahead of its pop
     uint32_t csr_pos = 0, csr_end = 0;                       // rest of the CSR list being expanded
     float f_max = FLT_MAX;
@@ -695,6 +695,8 @@ __device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64*
 
     if ((p.mode & 1) && p.q_slots[qi] == 0xffffffffu) {  // item absent -> Ok(None), reader.rs:826
         if (lane == 0) p.out_len[qi] = 0xffffffffu;
+        for (int i = lane; i < (int)count; i += 32) { p.out_ids[qi * count + i] = 0; p.out_dist[qi * count + i] = 0.0f; }
+        if (p.out_ctr && lane < HB_N_CTR) p.out_ctr[qi * HB_N_CTR + lane] = 0;
         return;
     }
 #ifdef HB_PHASES
@@ -799,10 +801,10 @@ __device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64*
         flags |= 0x100;
     }
     __syncwarp();
-    for (int i = lane; i < n_out; i += 32) {
-        u64 k = c.res[i];
-        p.out_ids[qi * count + i] = __ldg(&ix.ids[(uint32_t)k]);
-        p.out_dist[qi * count + i] = key_dist(k);
+    for (int i = lane; i < (int)count; i += 32) {  // entries past out_len are zeroed: the output is a function of the inputs
+        u64 k = i < n_out ? c.res[i] : 0;
+        p.out_ids[qi * count + i] = i < n_out ? __ldg(&ix.ids[(uint32_t)k]) : 0u;
+        p.out_dist[qi * count + i] = i < n_out ? key_dist(k) : 0.0f;
     }
     if (p.n_peers) {
         // fused all-gather: this shard's padded top-k of query qi goes straight into every peer's gather buffer

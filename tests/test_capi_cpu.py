@@ -173,3 +173,81 @@ def test_python_mirror_surface():
     s = hb.Searched([(1, 0.5)], False)
     assert s.into_nns() == [(1, 0.5)] and s.did_cancel() is False
     assert [d.name() for d in (hb.Euclidean, hb.Cosine, hb.Manhattan, hb.Hamming)] == ["euclidean", "cosine", "manhattan", "hamming"]
+
+
+def _roaring_with_runs(ids):
+    """RoaringFormatSpec, cookie 12347: every container run-encoded (what `optimize()`d bitmaps and other writers emit;
+    roaring-rs reads them too)."""
+    import struct
+    ids = sorted(set(int(i) for i in ids))
+    if not ids:
+        return struct.pack("<II", 12346, 0)
+    groups = {}
+    for i in ids:
+        groups.setdefault(i >> 16, []).append(i & 0xffff)
+    keys = sorted(groups)
+    n = len(keys)
+    out = struct.pack("<I", 12347 | ((n - 1) << 16)) + bytes([0xff] * ((n + 7) // 8))
+    bodies = []
+    for k in keys:
+        lo = groups[k]
+        runs, s, prev = [], lo[0], lo[0]
+        for v in lo[1:]:
+            if v != prev + 1:
+                runs.append((s, prev - s))
+                s = v
+            prev = v
+        runs.append((s, prev - s))
+        out += struct.pack("<HH", k, len(lo) - 1)
+        bodies.append(struct.pack("<H", len(runs)) + b"".join(struct.pack("<HH", a, b) for a, b in runs))
+    if n >= 4:  # NO_OFFSET_THRESHOLD
+        pos = len(out) + 4 * n
+        for b in bodies:
+            out += struct.pack("<I", pos)
+            pos += len(b)
+    return out + b"".join(bodies)
+
+
+def test_kv_decode_bitmap_and_run_containers():
+    """A dense index of more than 4096 ids per 64K chunk stores `items` as a Roaring BITMAP container (every real index
+    does); Links written by a run-optimising encoder use RUN containers.  Both decode to the same snapshot."""
+    n, dims = 9000, 4
+    ids = np.concatenate([np.arange(n - 3, dtype=np.uint32), np.array([70000, 70001, 200000], np.uint32)])
+    db, x = make_db("euclidean", n, dims, seed=2, ids=ids, M=6, M0=12, efc=24, n_threads=4)
+    kv = [(bytes(k), bytes(v)) for k, v in db.export_kv(0)]
+    meta = [v for k, v in kv if k[2] == 0 and k[3:7] == b"\0\0\0\0"][0]
+    roaring = meta[len(b"euclidean") + 1 + 8:]
+    assert roaring[:4] == (12346).to_bytes(4, "little")   # no-run cookie; first container card 8997 > 4096 -> bitmap
+    from oracle import oracle as O
+    lib = L.lib()
+    handles = []
+    for rewrite in (False, True):
+        h = _begin(0)
+        for k, v in kv:
+            if rewrite and k[2] == 2:      # Links: [1][roaring] -> same set, run containers
+                v = b"\x01" + _roaring_with_runs(O.roaring_deserialize(v[1:]))
+            if rewrite and k[2] == 0 and k[3:7] == b"\0\0\0\0":  # metadata `items`, run-encoded (3 containers)
+                name_end = v.index(b"\0") + 1
+                items_size = int.from_bytes(v[name_end + 4:name_end + 8], "big")
+                r = _roaring_with_runs(ids)
+                v = v[:name_end + 4] + len(r).to_bytes(4, "big") + r + v[name_end + 8 + items_size:]
+            assert lib.hb_index_push_kv(h, k, len(k), v, len(v)) == L.HB_OK, lib.hb_last_error()
+        assert lib.hb_index_finalize(h, 0) in (L.HB_OK, L.HB_ECUDA), lib.hb_last_error()
+        got = np.zeros(n, np.uint32)
+        assert lib.hb_index_n_items(h) == n
+        lib.hb_index_item_ids(h, got.ctypes.data_as(C.c_void_p), n)
+        assert np.array_equal(got, ids)
+        handles.append(h)
+    # identical snapshots: the cache files are byte-identical
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        blobs = []
+        for i, h in enumerate(handles):
+            fn = os.path.join(d, f"s{i}.hb").encode()
+            assert lib.hb_index_save(h, fn) == L.HB_OK
+            blobs.append(open(fn, "rb").read())
+            lib.hb_index_free(h)
+        assert blobs[0] == blobs[1]
+    # 5 containers -> the run cookie carries an offset header
+    many = np.array([1, 2, 3, 65536 + 9, 3 * 65536 + 1, 3 * 65536 + 2, 9 * 65536, 11 * 65536 + 5], np.uint32)
+    assert np.array_equal(O.roaring_deserialize(_roaring_with_runs(many)), many)

@@ -49,7 +49,9 @@ def test_candidates_filter_graph_walk_and_linear_scan(metric, dims):
             assert_same(got, want, what)
             assert_counters_same(got[3], want[3], what)
             assert np.array_equal(got[3][:, 6] & 3, want[3][:, 6] & 3), what  # FALLBACK / LINEAR flags
-            assert set(got[0][got[0] != 0].ravel().tolist()) <= set(cand.tolist()) | {0}
+            valid = np.arange(count)[None, :] < got[2][:, None]
+            assert set(got[0][valid].tolist()) <= set(cand.tolist())
+            assert not got[0][~valid].any() and not got[1][~valid].any()   # nothing stale past out_len
     # disjoint candidates -> [] (reader.rs:654-656); empty bitmap likewise
     for c in (np.array([0, 2], np.uint32), np.zeros(0, np.uint32)):
         ids_, dist_, lens_ = rd.nns(10).candidates(c).by_vectors_raw(q)
