@@ -21,7 +21,8 @@ FLAGS = [
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false", "-split-compile", "0",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function",
 ]
-VARIANTS = {"": [], "phases": ["-DHB_PHASES"], "trace": ["-DHB_TRACE"], "rg2": ["-DHB_ROW_GROUP=2"]}
+VARIANTS = {"": [], "phases": ["-DHB_PHASES"], "trace": ["-DHB_TRACE"], "rg2": ["-DHB_ROW_GROUP=2"],
+            "bin5": ["-DHB_MIN_BLOCKS_BIN=5"], "bin6": ["-DHB_MIN_BLOCKS_BIN=6"], "bin8": ["-DHB_MIN_BLOCKS_BIN=8"]}
 
 
 def out_path(variant=""):

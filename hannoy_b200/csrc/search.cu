@@ -17,6 +17,7 @@
 //     heaps in global memory (never on the CPU).
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
 
 #include "dist.cuh"
 #include "ring.cuh"
@@ -27,6 +28,9 @@
 #endif
 #ifndef HB_MIN_BLOCKS_DIRECT
 #define HB_MIN_BLOCKS_DIRECT 4
+#endif
+#ifndef HB_MIN_BLOCKS_BIN
+#define HB_MIN_BLOCKS_BIN 4  // binary codes: one lane per row, no ring -> shared memory is not the limit, registers are
 #endif
 #ifndef HB_MIN_BLOCKS_F32
 #define HB_MIN_BLOCKS_F32 3  // resident CTAs per SM the f32 kernel is compiled for (register budget)
@@ -201,7 +205,13 @@ __device__ __forceinline__ void vis_clear(Ctx& c) {
     if (c.touched_over) {
         for (uint32_t w = lane_id(); w < c.p.vis_words; w += 32) c.vis[w] = 0;
     } else {
-        for (uint32_t i = lane_id(); i < c.touched_len; i += 32) c.vis[c.touched[i] >> 5] = 0;
+        // the list reads are independent of each other: four in flight per lane instead of one
+        uint32_t i = lane_id();
+        for (; i + 96 < c.touched_len; i += 128) {
+            const uint32_t t0 = c.touched[i], t1 = c.touched[i + 32], t2 = c.touched[i + 64], t3 = c.touched[i + 96];
+            c.vis[t0 >> 5] = 0; c.vis[t1 >> 5] = 0; c.vis[t2 >> 5] = 0; c.vis[t3 >> 5] = 0;
+        }
+        for (; i < c.touched_len; i += 32) c.vis[c.touched[i] >> 5] = 0;
     }
     c.touched_len = 0;
     c.touched_over = false;
@@ -383,7 +393,8 @@ __device__ __forceinline__ void heaps_stage_queue(Ctx& c, const ChunkUpdate& u, 
         }
         if (c.q_len + mq - d0 > c.q_cap) { c.overflow = true; return; }  // would have to drop a live entry
     }
-    if (mq || prune)
+    // nothing to insert and no dead entry at the front (they form a prefix of the descending array): the queue is unchanged
+    if (mq || (prune && c.q_len > 0 && (uint32_t)(c.que[0] >> 32) > mb))
         c.q_len = merge_batch<true, true, MERGE_TILES>(c.que, c.q_len, qhas, ((u64)u.bits << 32) | (uint32_t)(~u.s), c.q_cap, mb);
 }
 
@@ -840,7 +851,7 @@ __device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64*
 
 // Shared memory of one warp: [row ring][ring barriers][query][heaps (pass 0 only)].
 template <int KIND>
-__global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, KIND == KIND_F32_WARP ? HB_MIN_BLOCKS_F32 : (KIND == KIND_F32_DIRECT ? HB_MIN_BLOCKS_DIRECT : 4)) hnsw_search_kernel(const __grid_constant__ SearchParams p) {
+__global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, KIND == KIND_F32_WARP ? HB_MIN_BLOCKS_F32 : (KIND == KIND_F32_DIRECT ? HB_MIN_BLOCKS_DIRECT : (KIND == KIND_BIN ? HB_MIN_BLOCKS_BIN : 4))) hnsw_search_kernel(const __grid_constant__ SearchParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp_in_block = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
@@ -994,6 +1005,8 @@ hb_status launch_search(const SearchParams& fast, const SearchParams& slow, int 
         uint64_t need = ((uint64_t)fast.n_work + wpb - 1) / wpb;
         int blocks = (uint64_t)blocks_fast > need ? (int)need : blocks_fast;
         if (blocks < 1) blocks = 1;
+        static const bool dbg = getenv("HB_DEBUG_LAUNCH") != nullptr;
+        if (dbg) fprintf(stderr, "[hb] search launch: kind %d, %d CTAs x %d threads, %zu B shared memory per CTA, res_cap %u q_cap %u\n", variant_of(fast), blocks, wpb * 32, smem, fast.res_cap, fast.q_cap);
         kernel_for(variant_of(fast))<<<blocks, wpb * 32, smem, stream>>>(fast);
         ++g_launches;
     } else {

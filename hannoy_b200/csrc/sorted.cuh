@@ -83,7 +83,7 @@ template <bool DESC, bool TRIM, int MAX_TILES>
 __device__ HB_MERGE_INLINE int merge_batch(u64* a, int len, bool has, u64 key, int keep, uint32_t drop_above) {
     const int lane = lane_id();
     const unsigned hm = __ballot_sync(FULL, has);
-    int pos = 0;
+    int pos = 0x7fffffff;
     if (has) {
         int lo = 0, hi = len;
         while (lo < hi) {
@@ -94,6 +94,10 @@ __device__ HB_MERGE_INLINE int merge_batch(u64* a, int len, bool has, u64 key, i
         }
         pos = lo;
     }
+    // Entries below the smallest insertion point do not move (unless the front is trimmed): their tiles are neither
+    // loaded nor stored.  Dead entries form a prefix of a descending array, so a[0] tells whether there is any.
+    const bool trim = TRIM && len > 0 && (uint32_t)(a[0] >> 32) > drop_above;
+    const int t0 = trim ? 0 : (int)(__reduce_min_sync(FULL, (unsigned)pos) >> 5);
     u64 v[MAX_TILES];
     int sh[MAX_TILES];
     int d = 0;
@@ -102,11 +106,12 @@ __device__ HB_MERGE_INLINE int merge_batch(u64* a, int len, bool has, u64 key, i
         int i = t * 32 + lane;
         v[t] = 0ull;
         sh[t] = 0;
-        if (t * 32 < len) {  // warp-uniform
+        if (t >= t0 && t * 32 < len) {  // warp-uniform
             if (i < len) v[t] = a[i];
-            if (TRIM) d += __popc(__ballot_sync(FULL, i < len && (uint32_t)(v[t] >> 32) > drop_above));
+            if (TRIM) { if (trim) d += __popc(__ballot_sync(FULL, i < len && (uint32_t)(v[t] >> 32) > drop_above)); }
         }
     }
+    if (!has) pos = 0;
     int rank = 0;
     for (unsigned m = hm; m; m &= m - 1) {
         int src = __ffs(m) - 1;
@@ -115,7 +120,7 @@ __device__ HB_MERGE_INLINE int merge_batch(u64* a, int len, bool has, u64 key, i
         rank += DESC ? (kb > key) : (kb < key);
 #pragma unroll
         for (int t = 0; t < MAX_TILES; ++t)
-            if (t * 32 < len) sh[t] += (pb <= t * 32 + lane);
+            if (t >= t0 && t * 32 < len) sh[t] += (pb <= t * 32 + lane);
     }
     __syncwarp();
     const int new_len = min(len + __popc(hm) - d, keep);
@@ -123,7 +128,7 @@ __device__ HB_MERGE_INLINE int merge_batch(u64* a, int len, bool has, u64 key, i
     for (int t = 0; t < MAX_TILES; ++t) {
         int i = t * 32 + lane;
         int j = i + sh[t] - d;
-        if (t * 32 < len && i < len && j >= 0 && j < new_len) a[j] = v[t];
+        if (t >= t0 && t * 32 < len && i < len && j >= 0 && j < new_len) a[j] = v[t];
     }
     if (has) {
         int j = pos + rank - d;
