@@ -218,6 +218,18 @@ def algorithmic_bytes(ctr, w):
     return vec + adj, vec
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -240,6 +252,13 @@ def main():
 
     def log(msg):
         print(f"[bench r{rank}] {msg}", file=sys.stderr, flush=True)
+
+    # stdout carries exactly one JSON line (rank 0): anything a library prints there (NCCL's version banner when the box
+    # sets NCCL_DEBUG, torch warnings) is sent to stderr instead; emit() writes the line to the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     have_cuda = torch.cuda.is_available()
@@ -444,7 +463,7 @@ def main():
             "cpu_baseline": {"value": round(n_cpu / t_cpu, 1), "unit": "queries/s", "cores": threads, "kind": "port",
                              "sample": f"first {n_cpu} queries of the batch, ef_search={ef_pick}, oracle port on {threads} threads"},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if use_dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -463,7 +482,7 @@ def run_sharded(args, w, rank, world, local_rank, dev, use_dist, threads, log):
     from oracle.oracle import OracleDb
     if not use_dist:
         if args.impl == "reference":
-            print(json.dumps({"impl": "reference", "unavailable": "the sharded workload has no single-process CPU arm; use the default workload"}))
+            emit({"impl": "reference", "unavailable": "the sharded workload has no single-process CPU arm; use the default workload"})
             return 0
         dist.init_process_group("nccl" if dev.type == "cuda" else "gloo", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1,
                                 **({"device_id": dev} if dev.type == "cuda" else {}))
@@ -524,7 +543,7 @@ def run_sharded(args, w, rank, world, local_rank, dev, use_dist, threads, log):
                            "fused_equals_nccl": same, "parity_vs_oracle": "bit-exact" if parity_ok else "MISMATCH",
                            "cache": "inputs larger than L2"},
                 "gpu_launches": int(launches)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     dist.barrier()
     ss.close_fused()
     dist.destroy_process_group()
@@ -565,7 +584,7 @@ def run_reference(args, w, db, x_host, q_host, threads, config, log):
                          "sample": f"{n_s} queries per step, oracle port on {threads} threads"},
         "e2e": {"value": round(qps, 1), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
