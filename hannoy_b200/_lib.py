@@ -20,7 +20,7 @@ LEN_CANCELLED, LEN_NONE = 0x80000000, 0xFFFFFFFF
 # every symbol include/hannoy_b200.h declares
 EXPORTS = [
     "hb_metric_name", "hb_metric_from_name", "hb_index_begin", "hb_index_push_kv", "hb_index_push_lmdb", "hb_index_open_lmdb",
-    "hb_lmdb_scan", "hb_index_save", "hb_index_load", "hb_index_from_arrays",
+    "hb_lmdb_scan", "hb_index_save", "hb_index_load", "hb_index_build_graph", "hb_index_export_kv", "hb_index_from_arrays",
     "hb_index_finalize", "hb_index_free", "hb_index_dimensions", "hb_index_n_items", "hb_index_n_entry_points",
     "hb_index_max_level", "hb_index_version", "hb_index_item_ids", "hb_index_contains_item", "hb_index_item_vector",
     "hb_search_by_vector", "hb_search_by_item", "hb_search_by_vector_device", "hb_exact_knn", "hb_merge_topk_device",
@@ -34,6 +34,11 @@ class QueryOpts(C.Structure):
     _fields_ = [("candidates", C.c_void_p), ("n_candidates", C.c_uint64), ("has_candidates", C.c_int),
                 ("linear_below", C.c_uint32), ("linear_below_ratio", C.c_float),
                 ("cancel", C.c_void_p), ("cancel_after_polls", C.c_uint64)]
+
+
+class BuildOpts(C.Structure):
+    _fields_ = [("M", C.c_uint32), ("M0", C.c_uint32), ("ef_construction", C.c_uint32), ("alpha", C.c_float),
+                ("seed", C.c_uint64), ("batch_max", C.c_uint32)]
 
 
 KV_VISIT = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_ubyte), C.c_size_t, C.POINTER(C.c_ubyte), C.c_size_t)
@@ -56,6 +61,8 @@ def lib():
         "hb_metric_name": (C.c_char_p, [i32]), "hb_metric_from_name": (i32, [C.c_char_p]),
         "hb_index_begin": (i32, [i32, u16, C.POINTER(vp)]),
         "hb_index_push_kv": (i32, [vp, C.c_char_p, sz, C.c_char_p, sz]),
+        "hb_index_build_graph": (i32, [vp, C.POINTER(BuildOpts), i32, vp]),
+        "hb_index_export_kv": (i32, [vp, i32, KV_VISIT, vp]),
         "hb_index_save": (i32, [vp, C.c_char_p]), "hb_index_load": (i32, [vp, C.c_char_p]),
         "hb_index_push_lmdb": (i32, [vp, C.c_char_p, C.c_char_p, C.POINTER(u64)]),
         "hb_index_open_lmdb": (i32, [C.c_char_p, C.c_char_p, i32, u16, i32, C.POINTER(vp)]),

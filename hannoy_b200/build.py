@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["capi.cu", "search.cu", "exact.cu", "snapshot.cpp", "lmdb_walk.cpp"]
+SOURCES = ["capi.cu", "search.cu", "exact.cu", "build.cu", "snapshot.cpp", "lmdb_walk.cpp"]
 HEADERS = ["common.h", "dist.cuh", "sorted.cuh", "ring.cuh", os.path.join("..", "..", "include", "hannoy_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -22,7 +22,7 @@ FLAGS = [
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function",
 ]
 VARIANTS = {"": [], "phases": ["-DHB_PHASES"], "trace": ["-DHB_TRACE"], "rg2": ["-DHB_ROW_GROUP=2"],
-            "bin5": ["-DHB_MIN_BLOCKS_BIN=5"], "bin6": ["-DHB_MIN_BLOCKS_BIN=6"], "bin8": ["-DHB_MIN_BLOCKS_BIN=8"]}
+            "bdebug": ["-DHB_BUILD_DEBUG"], "batomic": ["-DHB_BUILD_ATOMIC_LISTS"], "bin5": ["-DHB_MIN_BLOCKS_BIN=5"], "bin6": ["-DHB_MIN_BLOCKS_BIN=6"], "bin8": ["-DHB_MIN_BLOCKS_BIN=8"]}
 
 
 def out_path(variant=""):

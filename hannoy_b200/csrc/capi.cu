@@ -167,6 +167,46 @@ hb_status hb_index_open_lmdb(const char* path, const char* db_name, hb_metric m,
     return st;
 }
 
+// ---- device graph builder (build.cu) and write-back ------------------------------------------------------------------
+hb_status hb_index_build_graph(hb_index* ix, const hb_build_opts* opts, int device, uint64_t* stats_out) {
+    if (!ix) { set_error("hb_index_build_graph: null argument"); return HB_EINVAL; }
+    if (ix->finalized) { set_error("index already finalized"); return HB_ESTATE; }
+    try {
+        if (ix->ids.empty() && (ix->have_metadata || !ix->kv_items.empty())) {   // items came through push_kv / push_lmdb
+            ix->need_build = false;                                                // building is what this call is for
+            hb_status st = build_host_snapshot_from_kv(ix);
+            if (st != HB_OK) return st;
+        }
+        hb_build_opts o = {16, 32, 100, 1.0f, 42, 0};
+        if (opts) o = *opts;
+        if (ix->version[0] == 0 && ix->version[1] == 0 && ix->version[2] == 0) { ix->version[1] = 1; ix->version[2] = 3; }
+        return build_graph_on_device(ix, o.M, o.M0, o.ef_construction, o.alpha, o.seed, o.batch_max, device, stats_out);
+    } catch (const std::bad_alloc&) {
+        return HB_ENOMEM;
+    }
+}
+
+struct ExportCtx { hb_kv_visit fn; void* user; };
+static int export_cb(void* u, const uint8_t* k, size_t kl, const uint8_t* v, size_t vl) {
+    ExportCtx* c = (ExportCtx*)u;
+    return c->fn(c->user, k, kl, v, vl);
+}
+hb_status hb_index_export_kv(const hb_index* ix, int with_items, hb_kv_visit fn, void* user) {
+    if (!ix || !fn) { set_error("hb_index_export_kv: null argument"); return HB_EINVAL; }
+    if (!ix->finalized && (ix->ids.empty() || !ix->kv_items.empty() || !ix->kv_links.empty())) {
+        set_error("hb_index_export_kv: the index holds no decoded snapshot yet");
+        return HB_ESTATE;
+    }
+    try {
+        ExportCtx c{fn, user};
+        hb_status st = export_kv(ix, with_items != 0, export_cb, &c);
+        if (st == HB_ESTATE) set_error("hb_index_export_kv: stopped by the visitor");
+        return st;
+    } catch (const std::bad_alloc&) {
+        return HB_ENOMEM;
+    }
+}
+
 // ---- flat-file snapshot cache (snapshot.cpp) ----------------------------------------------------------------------
 hb_status hb_index_save(const hb_index* ix, const char* path) {
     if (!ix || !path) { set_error("hb_index_save: null argument"); return HB_EINVAL; }
@@ -209,7 +249,8 @@ hb_status hb_index_from_arrays(hb_index* ix, uint32_t dims, const uint32_t* ids,
     if (ix->finalized) { set_error("index already finalized"); return HB_ESTATE; }
     if (n >= 0xffffffffull) { set_error("too many items"); return HB_EINVAL; }
     if (n && (!ids || !rows)) { set_error("hb_index_from_arrays: null ids/rows"); return HB_EINVAL; }
-    if (n_layers > (uint32_t)MAX_LEVELS || (n && max_level >= n_layers)) { set_error("bad layer count"); return HB_EINVAL; }
+    // n_layers == 0: items only, the graph is still to be built (hb_index_build_graph)
+    if (n_layers > (uint32_t)MAX_LEVELS || (n && n_layers && max_level >= n_layers) || (!n_layers && (n_ep || max_level))) { set_error("bad layer count"); return HB_EINVAL; }
     try {
         ix->dims = dims;
         ix->ids.assign(ids, ids + n);
@@ -251,6 +292,52 @@ hb_status hb_index_from_arrays(hb_index* ix, uint32_t dims, const uint32_t* ids,
 
 }  // extern "C"
 
+
+// Geometry of the device row layout + the rows themselves (natural encoding uploaded in slabs, re-laid out on the
+// device).  Shared by hb_index_finalize and the device graph builder.  The current device must be set.
+hb_status hb::setup_dev_rows(hb_index* ix, DevIndex& d, std::vector<void*>& allocs) {
+    size_t n = ix->ids.size();
+    d.n = (uint32_t)n;
+    d.dims = ix->dims;
+    d.metric = (int)ix->metric;
+    d.kind = kind_for(ix->metric, ix->dims);
+    d.row_stride = device_row_stride(d.kind, ix->dims);
+    if (d.kind == KIND_F32_WARP) {
+        uint32_t blocks = ix->dims / 32;
+        d.n_chunks = (blocks + 3) / 4;
+        d.tail = ix->dims % 32;
+        d.tail_off = d.n_chunks * 128;
+    }
+    d.n_words = (ix->dims + 63) / 64;
+    if (n) {
+        void* drows = nullptr;
+        CUDA_TRY(cudaMalloc(&drows, std::max<size_t>(n * (size_t)d.row_stride, 16)));
+        allocs.push_back(drows);
+        const size_t slab_rows = std::max<size_t>(1, (256u << 20) / std::max<size_t>(ix->host_row_bytes, 1));
+        void* stage = nullptr;
+        CUDA_TRY(cudaMalloc(&stage, slab_rows * ix->host_row_bytes));
+        for (size_t r0 = 0; r0 < n; r0 += slab_rows) {
+            size_t nr = std::min(slab_rows, n - r0);
+            if (cudaMemcpy(stage, ix->host_rows.data() + r0 * ix->host_row_bytes, nr * ix->host_row_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+                cudaFree(stage);
+                set_error("row upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return HB_ECUDA;
+            }
+            layout_rows_kernel<<<(unsigned)nr, 128>>>((const uint8_t*)stage, ix->host_row_bytes,
+                                                      (uint8_t*)drows + r0 * (size_t)d.row_stride, d.row_stride, nr, ix->dims, d.kind);
+            ++g_launches;
+            if (cudaDeviceSynchronize() != cudaSuccess) {
+                cudaFree(stage);
+                set_error("row layout failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return HB_ECUDA;
+            }
+        }
+        cudaFree(stage);
+        d.rows = (const uint8_t*)drows;
+    }
+    return HB_OK;
+}
+
 template <class T>
 static hb_status upload(hb_index* ix, const T* host, size_t count, const T** out) {
     void* d = nullptr;
@@ -286,40 +373,10 @@ hb_status hb_index_finalize(hb_index* ix, int device) {
     ix->device = device;
     DevIndex& d = ix->dev;
     size_t n = ix->ids.size();
-    d.n = (uint32_t)n;
-    d.dims = ix->dims;
-    d.metric = (int)ix->metric;
-    d.kind = kind_for(ix->metric, ix->dims);
-    d.row_stride = device_row_stride(d.kind, ix->dims);
-    if (d.kind == KIND_F32_WARP) {
-        uint32_t blocks = ix->dims / 32;
-        d.n_chunks = (blocks + 3) / 4;
-        d.tail = ix->dims % 32;
-        d.tail_off = d.n_chunks * 128;
-    }
-    d.n_words = (ix->dims + 63) / 64;
+    if ((st = setup_dev_rows(ix, d, ix->dev_allocs)) != HB_OK) return st;
     d.max_level = ix->max_level;
     d.n_layers = (uint32_t)ix->layers.size();
     if (d.n_layers > (uint32_t)MAX_LEVELS) { set_error("too many layers"); return HB_EINVAL; }
-    if (n) {
-        // rows: upload natural encoding in slabs, re-layout on the device
-        void* drows = nullptr;
-        CUDA_TRY(cudaMalloc(&drows, std::max<size_t>(n * (size_t)d.row_stride, 16)));
-        ix->dev_allocs.push_back(drows);
-        const size_t slab_rows = std::max<size_t>(1, (256u << 20) / std::max<size_t>(ix->host_row_bytes, 1));
-        void* stage = nullptr;
-        CUDA_TRY(cudaMalloc(&stage, slab_rows * ix->host_row_bytes));
-        for (size_t r0 = 0; r0 < n; r0 += slab_rows) {
-            size_t nr = std::min(slab_rows, n - r0);
-            CUDA_TRY(cudaMemcpy(stage, ix->host_rows.data() + r0 * ix->host_row_bytes, nr * ix->host_row_bytes, cudaMemcpyHostToDevice));
-            layout_rows_kernel<<<(unsigned)nr, 128>>>((const uint8_t*)stage, ix->host_row_bytes,
-                                                      (uint8_t*)drows + r0 * (size_t)d.row_stride, d.row_stride, nr, ix->dims, d.kind);
-            ++g_launches;
-            CUDA_TRY(cudaDeviceSynchronize());
-        }
-        cudaFree(stage);
-        d.rows = (const uint8_t*)drows;
-    }
     if ((st = upload(ix, ix->host_hdr.data(), n, &d.hdr)) != HB_OK) return st;
     if ((st = upload(ix, ix->ids.data(), n, &d.ids)) != HB_OK) return st;
     for (uint32_t l = 0; l < d.n_layers; ++l) {

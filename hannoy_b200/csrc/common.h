@@ -98,8 +98,25 @@ struct SearchParams {
     const uint32_t* cancel_flag = nullptr;
     uint32_t cancel_after = 0;
     int linear_cancelled = 0;
+    int no_trim = 0;                   // graph builder, metrics with negative distances: shared-memory heaps without dead-entry trimming,
+                                       // no deferred pops (the literal reference loop); a negative distance does not end the walk
     int defer = 1;                     // layer 0, pass 0: overlap a chunk's heap update with the next pop's adjacency / visited traffic
 };
+// One batch of the device graph builder's candidate search (search.cu build_search_kernel): `walk_layer` of
+// src/hnsw.rs:460-519 for every item of the batch on layer `level` with ef = efc, optionally preceded by the greedy
+// ef = 1 descent of `insert` (hnsw.rs:304-309).  The graph in `sp.ix` is not modified while the kernel runs.
+struct BuildSearchParams {
+    SearchParams sp;                 // index view, visited workspace, heap capacities, ring geometry; sp.q_slots = the batch's item slots
+    uint32_t n_items = 0;
+    uint32_t level = 0, efc = 0;
+    int descend = 0;                 // 1: start at sp.ix.eps and descend max_level .. level + 1; 0: start at eps_in
+    const uint32_t* eps_in = nullptr;  // [n_items][eps_stride] slots, UINT32_MAX padded (the neighbours selected one layer above)
+    uint32_t eps_stride = 0;
+    unsigned long long* cand = nullptr;  // [n_items][efc] ascending (distance bits << 32 | slot)
+    uint32_t* cand_len = nullptr;        // [n_items]
+    unsigned long long* n_cut = nullptr; // walks that stopped early (heap capacity / negative distance in the pruning pass)
+};
+
 #ifndef HB_ROW_GROUP
 #define HB_ROW_GROUP 4
 #endif
@@ -164,6 +181,7 @@ struct hb_index {
     std::vector<hb::HostLayer> layers;
     std::vector<uint32_t> eps;      // slots
     uint32_t max_level = 0;
+    std::vector<uint32_t> node_level;  // per slot, set by the device graph builder: the item has a Links node on layers 0..node_level
     // --- device ---
     hb::DevIndex dev;
     std::vector<void*> dev_allocs;
@@ -180,6 +198,13 @@ hb_status build_host_snapshot_from_kv(hb_index* ix);
 bool roaring_decode(const uint8_t* p, size_t len, std::vector<uint32_t>& out);
 int64_t slot_of(const hb_index* ix, uint32_t id);
 hb_status snapshot_save(const hb_index* ix, const char* path);
+void roaring_encode(const uint32_t* sorted_ids, size_t n, std::vector<uint8_t>& out);
+typedef int (*kv_emit_fn)(void* user, const uint8_t* key, size_t klen, const uint8_t* val, size_t vlen);
+hb_status export_kv(const hb_index* ix, bool with_items, kv_emit_fn fn, void* user);
+// capi.cu / build.cu
+hb_status setup_dev_rows(hb_index* ix, DevIndex& d, std::vector<void*>& allocs);
+hb_status build_graph_on_device(hb_index* ix, uint32_t M, uint32_t M0, uint32_t efc, float alpha, uint64_t seed, uint32_t batch_max, int device,
+                                uint64_t* stats);
 hb_status snapshot_load(hb_index* ix, const uint8_t* data, size_t size);
 // lmdb_walk.cpp: in-order walk of one database of an LMDB data file, restricted to keys starting with `prefix`
 typedef hb_status (*lmdb_visit_fn)(void* user, const uint8_t* key, size_t klen, const uint8_t* val, size_t vlen, unsigned node_flags);
@@ -195,6 +220,8 @@ constexpr int SEARCH_MAX_SMEM = 226 * 1024;  // per SM (227 KB usable, 1 KB rese
 hb_status launch_search(const SearchParams& fast, const SearchParams& slow, int blocks_fast, int blocks_slow, void* stream);
 size_t search_smem_per_warp(const SearchParams& p);
 int search_blocks_per_sm(const SearchParams& p);  // resident CTAs per SM for these parameters
+hb_status launch_build_search(const BuildSearchParams& bp, int blocks, void* stream);
+int build_search_blocks_per_sm(const SearchParams& p);
 // runtime tunables (hb_tune): ring bytes per warp, max resident CTAs per SM, ...
 int tunable(const char* key, int dflt);
 // exact.cu

@@ -368,7 +368,7 @@ __device__ __forceinline__ void heaps_stage_res(Ctx& c, ChunkUpdate& u, int ef) 
         if (m_res) c.res_len = merge_batch<false, false, MERGE_TILES>(c.res, c.res_len, u.acc && u.pf, ((u64)u.bits << 32) | u.s, target, 0u);
     } else {
         const unsigned accm = __ballot_sync(FULL, u.acc && !u.qskip);
-        Heaps h{c.res, c.res_len, c.res_cap, c.que, c.q_len, c.q_cap, c.p.pass | (int)c.p.cancel_after, false};
+        Heaps h{c.res, c.res_len, c.res_cap, c.que, c.q_len, c.q_cap, c.p.pass | (int)c.p.cancel_after | c.p.no_trim, false};
         heaps_update_seq(&h, u.mode, ef, resm, accm, u.bits, u.s);
         c.res_len = h.res_len;
         c.q_len = h.q_len;
@@ -381,7 +381,7 @@ __device__ __forceinline__ void heaps_stage_queue(Ctx& c, const ChunkUpdate& u, 
     const int lane = lane_id();
     // Entries that can never be popped (is_dead, judged against the UPDATED result set) are not pushed, and old
     // ones — they sit at the front of the descending array — are trimmed in the same pass.
-    const bool prune = c.p.pass == 0 && !c.p.cancel_after && c.res_len >= ef && c.res_len > 0 && !(c.res[c.res_len - 1] >> 63);
+    const bool prune = c.p.pass == 0 && !c.p.cancel_after && !c.p.no_trim && c.res_len >= ef && c.res_len > 0 && !(c.res[c.res_len - 1] >> 63);
     const uint32_t mb = prune ? (uint32_t)(c.res[c.res_len - 1] >> 32) : 0xffffffffu;
     const bool qhas = u.acc && !u.qskip && !(prune && !(u.bits >> 31) && u.bits > mb);
     const int mq = __popc(__ballot_sync(FULL, qhas));
@@ -427,7 +427,7 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
     const uint32_t* off = ix.off[level];
     const uint32_t* nbr = ix.nbr[level];
     const uint32_t* nbrx = level == 0 ? ix.nbr0x : nullptr;
-    const bool defer = nbrx && c.p.pass == 0 && c.p.defer && !linear;  // a linear scan pops nothing (reader.rs:683-705)
+    const bool defer = nbrx && c.p.pass == 0 && c.p.defer && !linear && !c.p.no_trim;  // a linear scan pops nothing (reader.rs:683-705)
     uint32_t spec_cs = 0xffffffffu, spec_adj = 0xffffffffu;  // adjacency line requested ahead of its pop
     uint32_t csr_pos = 0, csr_end = 0;                       // rest of the CSR list being expanded
     float f_max = FLT_MAX;
@@ -558,7 +558,7 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
         const float dist = rows_finish<KIND>(c, rf, s);
         const uint32_t bits = __float_as_uint(dist);
         if (l01) PH_ADD(c, PH_ROWS)
-        if (mode != CH_LINEAR && c.p.pass == 0 && __ballot_sync(FULL, live && (bits >> 31))) { c.overflow = true; break; }
+        if (mode != CH_LINEAR && c.p.pass == 0 && !c.p.no_trim && __ballot_sync(FULL, live && (bits >> 31))) { c.overflow = true; break; }
         // ---- which points are accepted, and which of those may enter the result set (reader.rs:322,353,355-359) ----
         const bool pf = live && passes_filter(c, s, filt);
         bool acc = live;
@@ -888,6 +888,139 @@ __global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, KIND == KIND_F32_
         uint64_t qi = p.pass == 0 ? w : p.overflow_list[w];
         run_query<KIND>(p, qi, slot_idx, heap, qs, ring);
     }
+}
+
+// ---- device graph builder: candidate search --------------------------------------------------------------------------
+// One warp per item of the batch, the same visit() as the reader's walk: `walk_layer` (hnsw.rs:460-519) differs from
+// Visitor::visit only in that every call starts from an empty visited set and has no candidates filter.
+template <int KIND>
+__global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, KIND == KIND_F32_WARP ? HB_MIN_BLOCKS_F32 : (KIND == KIND_F32_DIRECT ? HB_MIN_BLOCKS_DIRECT : 4)) build_search_kernel(const __grid_constant__ BuildSearchParams bp) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const SearchParams& p = bp.sp;
+    const int warp_in_block = threadIdx.x >> 5;
+    const int warps_per_block = blockDim.x >> 5;
+    const int slot_idx = blockIdx.x * warps_per_block + warp_in_block;
+    const size_t ring_bytes = (size_t)p.ring_slots * p.ring_stride;
+    const size_t bar_bytes = ((size_t)p.ring_slots * 8 + 15) & ~(size_t)15;
+    const size_t heap_bytes = (size_t)(p.res_cap + p.q_cap) * 8;
+    const size_t per_warp = (ring_bytes + bar_bytes + p.q_smem_bytes + heap_bytes + 127) & ~(size_t)127;
+    unsigned char* base = smem + per_warp * warp_in_block;
+    float* qs = reinterpret_cast<float*>(base + ring_bytes + bar_bytes);
+    u64* heap = reinterpret_cast<u64*>(base + ring_bytes + bar_bytes + p.q_smem_bytes);
+    RowRing ring;
+    ring.ptr = base;
+    ring.data = smem_addr(base);
+    ring.bars = smem_addr(base + ring_bytes);
+    ring.slots = p.ring_slots;
+    ring.stride = p.ring_stride;
+    ring.phase = 0;
+    ring.policy = l2_policy_evict_first();
+    if (p.ring_slots) {
+        if (lane_id() == 0) {
+            for (uint32_t i = 0; i < p.ring_slots; ++i) mbar_init(ring.bars + i * 8, 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+    }
+    const DevIndex& ix = p.ix;
+    const int lane = lane_id();
+    for (;;) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(p.work_counter, 1ull);
+        w = __shfl_sync(FULL, w, 0);
+        if (w >= bp.n_items) break;
+        Ctx c(p, ring);
+        c.res = heap; c.res_cap = p.res_cap; c.res_len = 0;
+        c.que = heap + p.res_cap; c.q_cap = p.q_cap; c.q_len = 0;
+        c.vis = p.visited + (size_t)slot_idx * p.vis_words;
+        c.touched = p.touched + (size_t)slot_idx * p.touched_cap;
+        c.touched_len = 0; c.touched_over = false;
+        c.excl = 0xffffffffu; c.overflow = false;
+        c.cancelled = false; c.polls = 0;
+        c.tr = false;
+        c.n_dist_up = c.n_exp_up = c.n_deg_up = c.n_dist_l0 = c.n_exp_l0 = c.n_deg_l0 = 0;
+        c.cur_dist = c.cur_exp = c.cur_deg = 0;
+#ifdef HB_PHASES
+        for (int i = 0; i < PH_N; ++i) c.ph[i] = 0;
+#endif
+        stage_query<KIND>(c, qs, w);  // the item's own row (sp.mode = by_item, sp.q_slots = the batch)
+        const uint32_t* eps = nullptr;
+        uint32_t n_eps = 0, single = 0;
+        if (bp.descend) {
+            eps = ix.eps; n_eps = ix.n_ep;
+            for (uint32_t lvl = ix.max_level; lvl > bp.level && !c.overflow; --lvl) {  // hnsw.rs:304-309
+                visit<KIND>(c, eps, n_eps, single, lvl, 1, false, false, false);
+                if (c.res_len) { single = (uint32_t)c.res[0]; eps = nullptr; }
+                __syncwarp();
+                vis_clear(c);                                                          // walk_layer starts a fresh `visited`
+            }
+        } else {
+            eps = bp.eps_in + (size_t)w * bp.eps_stride;
+            uint32_t e = lane < (int)bp.eps_stride ? eps[lane] : 0xffffffffu;          // eps_stride <= 32
+            n_eps = __popc(__ballot_sync(FULL, e != 0xffffffffu));                     // valid entries come first
+        }
+        int n_out = 0;
+        if (eps == nullptr || n_eps > 0) {
+            c.overflow = false;
+            visit<KIND>(c, eps, n_eps, single, bp.level, (int)bp.efc, false, false, false);  // hnsw.rs:313-316
+            n_out = min(c.res_len, (int)bp.efc);  // an overflowing walk (cannot happen with these capacities) keeps what it has
+        }
+        __syncwarp();
+        for (int i = lane; i < n_out; i += 32) bp.cand[(size_t)w * bp.efc + i] = c.res[i];
+        if (lane == 0) {
+            bp.cand_len[w] = (uint32_t)n_out;
+            if (c.overflow && bp.n_cut) atomicAdd(bp.n_cut, 1ull);
+        }
+        vis_clear(c);
+        __syncwarp();
+    }
+}
+
+typedef void (*build_search_kernel_t)(const BuildSearchParams);
+static build_search_kernel_t build_kernel_for(int kind) {
+    switch (kind) {
+        case KIND_F32_WARP: return build_search_kernel<KIND_F32_WARP>;
+        case KIND_F32_DIRECT: return build_search_kernel<KIND_F32_DIRECT>;
+        case KIND_F32_LANE: return build_search_kernel<KIND_F32_LANE>;
+        default: return build_search_kernel<KIND_BIN>;
+    }
+}
+static int build_variant_of(const SearchParams& p) { return (p.ix.kind == KIND_F32_WARP && p.ring_slots == 0) ? KIND_F32_DIRECT : p.ix.kind; }
+static void set_build_kernel_attrs() {
+    static bool attr_set = false;
+    if (!attr_set) {
+        for (int k = 0; k < 4; ++k) cudaFuncSetAttribute(build_kernel_for(k), cudaFuncAttributeMaxDynamicSharedMemorySize, SEARCH_MAX_SMEM);
+        attr_set = true;
+    }
+}
+int build_search_blocks_per_sm(const SearchParams& p) {
+    set_build_kernel_attrs();
+    int nb = 0;
+    SearchParams q = p;
+    q.pass = 0;
+    size_t smem = search_smem_per_warp(q) * SEARCH_WARPS_PER_BLOCK;
+    if (smem > (size_t)SEARCH_MAX_SMEM) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, build_kernel_for(build_variant_of(p)), SEARCH_WARPS_PER_BLOCK * 32, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return nb;
+}
+hb_status launch_build_search(const BuildSearchParams& bp, int blocks, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    set_build_kernel_attrs();
+    SearchParams q = bp.sp;
+    q.pass = 0;
+    size_t smem = search_smem_per_warp(q) * SEARCH_WARPS_PER_BLOCK;
+    cudaMemsetAsync(bp.sp.work_counter, 0, sizeof(unsigned long long), stream);
+    uint32_t need = (bp.n_items + SEARCH_WARPS_PER_BLOCK - 1) / SEARCH_WARPS_PER_BLOCK;
+    if ((uint32_t)blocks > need) blocks = (int)need;
+    if (blocks < 1) blocks = 1;
+    build_kernel_for(build_variant_of(bp.sp))<<<blocks, SEARCH_WARPS_PER_BLOCK * 32, smem, stream>>>(bp);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("build search launch failed: %s", cudaGetErrorString(e)); return HB_ECUDA; }
+    return HB_OK;
 }
 
 std::atomic<unsigned long long> g_launches{0};

@@ -244,6 +244,108 @@ hb_status build_host_snapshot_from_kv(hb_index* ix) {
     return HB_OK;
 }
 
+// ---- writing a graph back in the reference's encoding --------------------------------------------------------------------
+// Roaring portable format without run containers (cookie 12346): what `RoaringBitmap::serialize_into` of roaring 0.10
+// emits for bitmaps that were never run-optimised (node.rs:143, metadata.rs:40): per 64K chunk an array container up to
+// 4096 values, a 1024 x u64 bitmap container above; descriptive header (key, cardinality - 1), then the offset header.
+void roaring_encode(const uint32_t* ids, size_t n, std::vector<uint8_t>& out) {
+    auto p16 = [&](uint32_t v) { out.push_back((uint8_t)v); out.push_back((uint8_t)(v >> 8)); };
+    auto p32 = [&](uint32_t v) { p16(v & 0xffff); p16(v >> 16); };
+    std::vector<std::pair<size_t, size_t>> runs;  // [begin, end) per container
+    for (size_t i = 0; i < n;) {
+        size_t j = i;
+        while (j < n && (ids[j] >> 16) == (ids[i] >> 16)) ++j;
+        runs.push_back({i, j});
+        i = j;
+    }
+    p32(12346);
+    p32((uint32_t)runs.size());
+    for (auto& r : runs) { p16(ids[r.first] >> 16); p16((uint32_t)(r.second - r.first - 1)); }
+    uint32_t offset = 8 + 8 * (uint32_t)runs.size();
+    for (auto& r : runs) {
+        p32(offset);
+        size_t card = r.second - r.first;
+        offset += card > 4096 ? 8192 : 2 * (uint32_t)card;
+    }
+    for (auto& r : runs) {
+        size_t card = r.second - r.first;
+        if (card > 4096) {
+            size_t at = out.size();
+            out.resize(at + 8192, 0);
+            for (size_t k = r.first; k < r.second; ++k) { uint32_t v = ids[k] & 0xffff; out[at + (v >> 3)] |= (uint8_t)(1u << (v & 7)); }
+        } else {
+            for (size_t k = r.first; k < r.second; ++k) p16(ids[k] & 0xffff);
+        }
+    }
+}
+
+// Every pair of the index in LMDB key order (key.rs:54-66, node_id.rs:11-21: Metadata < Updated < Links < Item), in the
+// encodings of metadata.rs:22-47, version.rs:33-46 and node.rs:130-149 — what `Writer::build` leaves in the database
+// (writer.rs:521-603, hnsw.rs:190-212), so that the CPU `Reader` can open a graph built on the device.
+hb_status export_kv(const hb_index* ix, bool with_items, kv_emit_fn fn, void* user) {
+    const size_t n = ix->ids.size();
+    auto key = [&](uint8_t mode, uint32_t item, uint8_t layer, uint8_t* k) {
+        k[0] = (uint8_t)(ix->index >> 8); k[1] = (uint8_t)ix->index; k[2] = mode;
+        k[3] = (uint8_t)(item >> 24); k[4] = (uint8_t)(item >> 16); k[5] = (uint8_t)(item >> 8); k[6] = (uint8_t)item; k[7] = layer;
+    };
+    auto be32p = [](std::vector<uint8_t>& v, uint32_t x) { v.push_back((uint8_t)(x >> 24)); v.push_back((uint8_t)(x >> 16)); v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x); };
+    uint8_t k[8];
+    std::vector<uint8_t> val, tmp;
+    // metadata
+    const char* name = hb_metric_name(ix->metric);
+    val.assign(name, name + std::strlen(name));
+    val.push_back(0);
+    be32p(val, ix->dims);
+    tmp.clear();
+    roaring_encode(ix->ids.data(), n, tmp);
+    be32p(val, (uint32_t)tmp.size());
+    val.insert(val.end(), tmp.begin(), tmp.end());
+    for (uint32_t s : ix->eps) { uint32_t id = ix->ids[s]; const uint8_t* b = (const uint8_t*)&id; val.insert(val.end(), b, b + 4); }  // ItemIds::raw_bytes: native endian
+    val.push_back((uint8_t)ix->max_level);
+    key(0, 0, 0, k);
+    if (fn(user, k, 8, val.data(), val.size())) return HB_ESTATE;
+    // version
+    val.clear();
+    for (int i = 0; i < 3; ++i) be32p(val, ix->version[i]);
+    key(0, 1, 0, k);
+    if (fn(user, k, 8, val.data(), val.size())) return HB_ESTATE;
+    // links: one node per (item, layer <= level of the item), keys ordered by item then layer.  A snapshot that did not
+    // come from the builder does not record levels: the highest layer with a link, or max_level for an entry point.
+    std::vector<uint32_t> lvl_of = ix->node_level;
+    if (lvl_of.size() != n) {
+        lvl_of.assign(n, 0);
+        for (uint32_t l = 1; l < ix->layers.size(); ++l)
+            for (size_t s = 0; s < n; ++s)
+                if (ix->layers[l].off[s + 1] > ix->layers[l].off[s]) lvl_of[s] = l;
+        for (uint32_t s : ix->eps) lvl_of[s] = std::max<uint32_t>(lvl_of[s], ix->max_level);
+    }
+    std::vector<uint32_t> ids;
+    for (size_t s = 0; s < n; ++s) {
+        for (uint32_t l = 0; l < ix->layers.size(); ++l) {
+            const HostLayer& hl = ix->layers[l];
+            if (lvl_of[s] < l) continue;
+            ids.clear();
+            for (uint64_t e = hl.off[s]; e < hl.off[s + 1]; ++e) ids.push_back(ix->ids[hl.nbr[e]]);  // slots ascending => ids ascending
+            val.assign(1, 1);  // LINKS_TAG
+            roaring_encode(ids.data(), ids.size(), val);
+            key(2, ix->ids[s], (uint8_t)l, k);
+            if (fn(user, k, 8, val.data(), val.size())) return HB_ESTATE;
+        }
+    }
+    if (with_items) {
+        const size_t hs = header_size(ix->metric);
+        for (size_t s = 0; s < n; ++s) {
+            val.assign(1 + hs, 0);  // NODE_TAG, header (norm; NodeHeaderHamming{idx: usize} is left 0)
+            if (hs == 4) std::memcpy(val.data() + 1, &ix->host_hdr[s], 4);
+            const uint8_t* row = ix->host_rows.data() + s * ix->host_row_bytes;
+            val.insert(val.end(), row, row + ix->host_row_bytes);
+            key(3, ix->ids[s], 0, k);
+            if (fn(user, k, 8, val.data(), val.size())) return HB_ESTATE;
+        }
+    }
+    return HB_OK;
+}
+
 // ---- flat-file snapshot cache ------------------------------------------------------------------------------------
 // The decoded host snapshot (what hb_index_finalize uploads) written as one flat little-endian file, so that a restart
 // does not walk LMDB and decode a roaring bitmap per node again.  The reference has no counterpart (its Reader reads

@@ -343,6 +343,45 @@ class Reader:
                                           C.byref(h)))
         return cls(h, d, index, device)
 
+    @classmethod
+    def build(cls, distance, dims, ids, rows, hdr, M=16, M0=32, ef_construction=100, alpha=1.0, seed=42, batch_max=0, index=0,
+              device=0, stats=None):
+        """HannoyBuilder::build on the device (hb_index_build_graph) over items given as flat arrays (rows / hdr as in
+        from_arrays), then Reader::open on the result.  `stats`: optional dict filled with batches / launches / max_level."""
+        d = _distance_of(distance)
+        lib = L.lib()
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        rows = np.ascontiguousarray(rows)
+        assert rows.dtype == (np.uint64 if d.is_binary() else np.float32)
+        hdr_a = None if hdr is None else np.ascontiguousarray(hdr, dtype=np.float32)
+        h = C.c_void_p()
+        _check(lib.hb_index_begin(d.ID, index, C.byref(h)))
+        try:
+            none_pp = (C.c_void_p * 1)()
+            _check(lib.hb_index_from_arrays(h, dims, _ptr(ids), len(ids), _ptr(rows), _ptr(hdr_a), 0, C.cast(none_pp, C.c_void_p),
+                                            C.cast(none_pp, C.c_void_p), None, 0, 0))
+            o = L.BuildOpts(M, M0, ef_construction, alpha, seed, batch_max)
+            st = np.zeros(8, np.uint64)
+            _check(lib.hb_index_build_graph(h, C.byref(o), device, _ptr(st)))
+            if stats is not None:
+                stats.update(batches=int(st[0]), launches=int(st[1]), items=int(st[2]), max_level=int(st[3]), dropped=int(st[4]), cut=int(st[5]))
+            _check(lib.hb_index_finalize(h, device))
+        except Exception:
+            lib.hb_index_free(h)
+            raise
+        return cls(h, d, index, device)
+
+    def export_kv(self, with_items=True):
+        """[(key, value)] in LMDB key order, in the encodings Writer::build writes (hb_index_export_kv)."""
+        out = []
+
+        def cb(user, k, kl, v, vl):
+            out.append((bytes(k[:kl]), bytes(v[:vl])))
+            return 0
+
+        _check(L.lib().hb_index_export_kv(self._h, int(with_items), L.KV_VISIT(cb), None))
+        return out
+
     def save(self, path):
         """Write the decoded snapshot to a flat cache file (hb_index_save); `Reader.load` brings it back without LMDB."""
         _check(L.lib().hb_index_save(self._h, os.fsencode(path)))

@@ -93,6 +93,30 @@ hb_status hb_lmdb_scan(const char* path, const char* db_name, const uint8_t* pre
 hb_status hb_index_save(const hb_index*, const char* path);
 hb_status hb_index_load(hb_index*, const char* path);
 
+/* ---- HannoyBuilder::build on the device (writer.rs:521-603 -> hnsw.rs:122-216; the GPU build the reference lists
+ * as missing, README.md:23-24) ---------------------------------------------------------------------------------
+ * For an index that holds items but no graph yet (hb_index_from_arrays with n_layers = 0, or the Item / Metadata pairs
+ * of a database whose `Writer` has not built): samples a level per item from the reference's distribution
+ * (hnsw.rs:94-120), inserts the items level group by level group in batches — candidate search (`walk_layer`),
+ * `robust_prune` and `add_link` in both directions run as kernels — and leaves per-layer links, entry points and
+ * max_level in the index.  hb_index_finalize then uploads it for searching; hb_index_export_kv hands it back in the
+ * reference's on-disk encoding.  Like the reference's rayon build the result depends on insertion interleaving: a
+ * valid hannoy graph of the same quality, not a bit-copy of a CPU build.  M <= 32, M0 <= 32.
+ * stats_out (optional): u64[8] = batches, kernel launches, items, max_level, reverse links dropped because more than 32
+ * arrived for one node in one batch, candidate walks cut short, 0, 0. */
+typedef struct {
+    uint32_t M, M0;            /* HannoyBuilder::<M, M0> const generics, 16 / 32 in the reference's docs and benches */
+    uint32_t ef_construction;  /* HannoyBuilder::ef_construction, default 100 (writer.rs) */
+    float alpha;               /* HannoyBuilder::alpha, default 1.0 */
+    uint64_t seed;             /* the `rng` argument of build() */
+    uint32_t batch_max;        /* most items in flight at once (0 = 4096); never more than 1/64 of the items already linked */
+} hb_build_opts;
+hb_status hb_index_build_graph(hb_index*, const hb_build_opts* opts /* NULL = defaults */, int device, uint64_t* stats_out);
+/* Every pair of the index in LMDB key order, in the encodings `Writer::build` writes (Metadata, Version, one Links node
+ * per (item, layer), and the Item nodes if with_items): `database.put(wtxn, key, value)` them and the CPU `Reader`
+ * opens the graph.  The pointers are valid during the callback only; a non-zero return stops the export. */
+hb_status hb_index_export_kv(const hb_index*, int with_items, hb_kv_visit fn, void* user);
+
 /* Route (b): flat arrays (bench / tests).  ids ascending & unique; rows = n x dims f32 (float
  * metrics) or n x ceil(dims/64) u64 code words (binary metrics); hdr = n header norms (Cosine,
  * BQ-Cosine) or NULL; per layer l: offsets[l] has n+1 u64 entries, nbrs[l] holds neighbour ITEM IDS,

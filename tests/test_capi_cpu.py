@@ -251,3 +251,50 @@ def test_kv_decode_bitmap_and_run_containers():
     # 5 containers -> the run cookie carries an offset header
     many = np.array([1, 2, 3, 65536 + 9, 3 * 65536 + 1, 3 * 65536 + 2, 9 * 65536, 11 * 65536 + 5], np.uint32)
     assert np.array_equal(O.roaring_deserialize(_roaring_with_runs(many)), many)
+
+
+@pytest.mark.parametrize("metric,dims,n,dense", [("cosine", 33, 600, False), ("hamming", 70, 300, False),
+                                                 ("binary quantized cosine", 100, 5000, False), ("euclidean", 8, 9000, True)])
+def test_export_kv_writes_the_reference_encoding(metric, dims, n, dense):
+    """hb_index_export_kv (metadata with array / bitmap containers, version, one Links node per (item, layer), items) is
+    byte for byte what the oracle's independent encoder of the reference format writes for the same graph — and feeding
+    it back through push_kv reproduces the snapshot."""
+    ids = np.arange(n, dtype=np.uint32) if dense else np.sort(np.random.default_rng(1).choice(1 << 22, n, replace=False)).astype(np.uint32)
+    db, x = make_db(metric, n, dims, seed=3, ids=ids, M=8, M0=16, efc=32, n_threads=4)
+    lib = L.lib()
+    d = hb.reader._distance_of(metric)
+    h = _begin(d.ID, index=5)
+    layers = db.layers()
+    offs = [np.ascontiguousarray(o, dtype=np.uint64) for o, _ in layers]
+    nbrs = [np.ascontiguousarray(b, dtype=np.uint32) for _, b in layers]
+    off_pp = (C.c_void_p * len(layers))(*[o.ctypes.data for o in offs])
+    nbr_pp = (C.c_void_p * len(layers))(*[b.ctypes.data for b in nbrs])
+    rows, hdr = np.ascontiguousarray(db.rows()), np.ascontiguousarray(db.headers(), dtype=np.float32)
+    eps = np.ascontiguousarray(db.entry_points, dtype=np.uint32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert lib.hb_index_from_arrays(h, dims, vp(ids), n, vp(rows), vp(hdr), len(layers), C.cast(off_pp, C.c_void_p),
+                                    C.cast(nbr_pp, C.c_void_p), vp(eps), len(eps), db.max_level) == L.HB_OK, lib.hb_last_error()
+    out = []
+
+    def cb(u, k, kl, v, vl):
+        out.append((bytes(k[:kl]), bytes(v[:vl])))
+        return 0
+    assert lib.hb_index_export_kv(h, 1, L.KV_VISIT(cb), None) == L.HB_OK, lib.hb_last_error()
+    want = [(bytes(k), bytes(v)) for k, v in db.export_kv(5)]
+    assert out == want
+    assert lib.hb_index_export_kv(h, 1, L.KV_VISIT(lambda *a: 1), None) == L.HB_ESTATE   # a visitor may stop it
+    g = _begin(d.ID, index=5)
+    _push_all(g, out)
+    assert lib.hb_index_finalize(g, 0) in (L.HB_OK, L.HB_ECUDA)
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        fa, fb = os.path.join(tmp, "a.hb").encode(), os.path.join(tmp, "b.hb").encode()
+        assert lib.hb_index_save(h, fa) == L.HB_OK and lib.hb_index_save(g, fb) == L.HB_OK
+        assert open(fa, "rb").read() == open(fb, "rb").read()
+    if not _has_gpu():   # the builder itself is device code: no CPU path
+        e = _begin(d.ID)
+        assert lib.hb_index_from_arrays(e, dims, vp(ids), n, vp(rows), vp(hdr), 0, None, None, None, 0, 0) == L.HB_OK
+        assert lib.hb_index_build_graph(e, None, 0, None) == L.HB_ECUDA
+        lib.hb_index_free(e)
+    lib.hb_index_free(g)
+    lib.hb_index_free(h)
