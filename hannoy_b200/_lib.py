@@ -38,7 +38,7 @@ class QueryOpts(C.Structure):
 
 class BuildOpts(C.Structure):
     _fields_ = [("M", C.c_uint32), ("M0", C.c_uint32), ("ef_construction", C.c_uint32), ("alpha", C.c_float),
-                ("seed", C.c_uint64), ("batch_max", C.c_uint32)]
+                ("seed", C.c_uint64), ("batch_max", C.c_uint32), ("dimensions", C.c_uint32)]
 
 
 KV_VISIT = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_ubyte), C.c_size_t, C.POINTER(C.c_ubyte), C.c_size_t)

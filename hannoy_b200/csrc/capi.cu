@@ -172,13 +172,25 @@ hb_status hb_index_build_graph(hb_index* ix, const hb_build_opts* opts, int devi
     if (!ix) { set_error("hb_index_build_graph: null argument"); return HB_EINVAL; }
     if (ix->finalized) { set_error("index already finalized"); return HB_ESTATE; }
     try {
+        hb_build_opts o = {16, 32, 100, 1.0f, 42, 0, 0};
+        if (opts) o = *opts;
         if (ix->ids.empty() && (ix->have_metadata || !ix->kv_items.empty())) {   // items came through push_kv / push_lmdb
+            if (!ix->have_metadata) {
+                // a database that was never built has no metadata yet (the Writer writes it in build(), writer.rs:521-603):
+                // every Item node is an item, the dimensions come from the caller
+                if (!o.dimensions) { set_error("hb_index_build_graph: the database has no metadata, pass hb_build_opts.dimensions"); return HB_EMISSING_METADATA; }
+                ix->meta_distance = hb_metric_name(ix->metric);
+                ix->meta_dims = o.dimensions;
+                ix->meta_items.clear();
+                for (auto& kv : ix->kv_items) ix->meta_items.push_back(kv.first);  // std::map: ascending
+                ix->meta_eps.clear();
+                ix->meta_max_level = 0;
+                ix->have_metadata = true;
+            }
             ix->need_build = false;                                                // building is what this call is for
             hb_status st = build_host_snapshot_from_kv(ix);
             if (st != HB_OK) return st;
         }
-        hb_build_opts o = {16, 32, 100, 1.0f, 42, 0};
-        if (opts) o = *opts;
         if (ix->version[0] == 0 && ix->version[1] == 0 && ix->version[2] == 0) { ix->version[1] = 1; ix->version[2] = 3; }
         return build_graph_on_device(ix, o.M, o.M0, o.ef_construction, o.alpha, o.seed, o.batch_max, device, stats_out);
     } catch (const std::bad_alloc&) {

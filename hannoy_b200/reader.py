@@ -360,7 +360,7 @@ class Reader:
             none_pp = (C.c_void_p * 1)()
             _check(lib.hb_index_from_arrays(h, dims, _ptr(ids), len(ids), _ptr(rows), _ptr(hdr_a), 0, C.cast(none_pp, C.c_void_p),
                                             C.cast(none_pp, C.c_void_p), None, 0, 0))
-            o = L.BuildOpts(M, M0, ef_construction, alpha, seed, batch_max)
+            o = L.BuildOpts(M, M0, ef_construction, alpha, seed, batch_max, 0)
             st = np.zeros(8, np.uint64)
             _check(lib.hb_index_build_graph(h, C.byref(o), device, _ptr(st)))
             if stats is not None:

@@ -110,6 +110,8 @@ typedef struct {
     float alpha;               /* HannoyBuilder::alpha, default 1.0 */
     uint64_t seed;             /* the `rng` argument of build() */
     uint32_t batch_max;        /* most items in flight at once (0 = 4096); never more than 1/64 of the items already linked */
+    uint32_t dimensions;       /* only for a database that was never built (no metadata pair yet): Writer::new(.., dimensions);
+                                  0 = take them from the metadata.  With metadata present the items are metadata.items. */
 } hb_build_opts;
 hb_status hb_index_build_graph(hb_index*, const hb_build_opts* opts /* NULL = defaults */, int device, uint64_t* stats_out);
 /* Every pair of the index in LMDB key order, in the encodings `Writer::build` writes (Metadata, Version, one Links node

@@ -179,6 +179,28 @@ class Reader {
         check(hb_index_open_lmdb(path, db_name, D::metric, index, device, &r.ix_));
         return r;
     }
+    // HannoyBuilder::build on the device (hb_index_build_graph) over the Item pairs of a database (metadata optional: pass
+    // opts.dimensions for a database that was never built), then Reader::open on the result.  export_kv() hands the
+    // Metadata / Links pairs back in the reference encoding for `database.put`.
+    template <class KvCursor>
+    static Reader build(const KvCursor& kv, uint16_t index, const hb_build_opts& opts, int device = 0) {
+        Reader r;
+        check(hb_index_begin(D::metric, index, &r.ix_));
+        for (const auto& [k, v] : kv)
+            check(hb_index_push_kv(r.ix_, (const uint8_t*)k.data(), k.size(), (const uint8_t*)v.data(), v.size()));
+        check(hb_index_build_graph(r.ix_, &opts, device, nullptr));
+        check(hb_index_finalize(r.ix_, device));
+        return r;
+    }
+    std::vector<std::pair<std::string, std::string>> export_kv(bool with_items) const {
+        std::vector<std::pair<std::string, std::string>> out;
+        auto cb = [](void* u, const uint8_t* k, size_t kl, const uint8_t* v, size_t vl) -> int {
+            ((std::vector<std::pair<std::string, std::string>>*)u)->emplace_back(std::string((const char*)k, kl), std::string((const char*)v, vl));
+            return 0;
+        };
+        check(hb_index_export_kv(ix_, with_items ? 1 : 0, cb, &out));
+        return out;
+    }
     Reader(Reader&& o) noexcept : ix_(o.ix_) { o.ix_ = nullptr; }
     Reader& operator=(Reader&& o) noexcept { std::swap(ix_, o.ix_); return *this; }
     Reader(const Reader&) = delete;

@@ -33,6 +33,18 @@ pub struct hb_query_opts {
 }
 pub const HB_LEN_CANCELLED: u32 = 0x8000_0000;
 
+#[repr(C)]
+pub struct hb_build_opts {
+    pub m: u32,
+    pub m0: u32,
+    pub ef_construction: u32,
+    pub alpha: f32,
+    pub seed: u64,
+    pub batch_max: u32,
+    pub dimensions: u32,
+}
+pub type hb_kv_visit = extern "C" fn(user: *mut c_void, key: *const u8, klen: usize, val: *const u8, vlen: usize) -> c_int;
+
 extern "C" {
     pub fn hb_metric_from_name(name: *const c_char) -> c_int;
     pub fn hb_index_begin(m: hb_metric, index: u16, out: *mut *mut hb_index) -> hb_status;
@@ -41,6 +53,8 @@ extern "C" {
     pub fn hb_index_open_lmdb(
         path: *const c_char, db_name: *const c_char, m: hb_metric, index: u16, device: c_int, out: *mut *mut hb_index,
     ) -> hb_status;
+    pub fn hb_index_build_graph(ix: *mut hb_index, opts: *const hb_build_opts, device: c_int, stats_out: *mut u64) -> hb_status;
+    pub fn hb_index_export_kv(ix: *const hb_index, with_items: c_int, f: hb_kv_visit, user: *mut c_void) -> hb_status;
     pub fn hb_cancel_token_create(device: c_int, out: *mut *mut hb_cancel_token) -> hb_status;
     pub fn hb_cancel_token_cancel(t: *mut hb_cancel_token) -> hb_status;
     pub fn hb_cancel_token_free(t: *mut hb_cancel_token);

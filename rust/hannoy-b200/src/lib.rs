@@ -103,6 +103,49 @@ impl<D: Distance> GpuReader<D> {
         Ok(GpuReader { raw, dimensions, device, _marker: PhantomData })
     }
 
+    /// `HannoyBuilder::build` on the GPU for a database whose items were added by `Writer::add_item` but whose graph is not
+    /// built (or is to be rebuilt): snapshots the Item pairs, builds on `device`, writes the Metadata and Links pairs back
+    /// through `wtxn` (what writer.rs:521-603 / hnsw.rs:190-212 write) and removes the `Updated` stones, then returns the
+    /// reader over the new graph.  `M` / `M0` are runtime values here (<= 32).
+    #[allow(clippy::too_many_arguments)]
+    pub fn build_and_open(
+        wtxn: &mut heed::RwTxn, index: u16, database: Database<D>, dimensions: usize, m: u32, m0: u32, ef_construction: u32, alpha: f32,
+        seed: u64, device: i32,
+    ) -> Result<Self> {
+        let name = CString::new(D::name()).unwrap();
+        let metric = unsafe { ffi::hb_metric_from_name(name.as_ptr()) };
+        let mut raw = std::ptr::null_mut();
+        check(unsafe { ffi::hb_index_begin(metric, index, &mut raw) }, (0, 0))?;
+        let this = GpuReader { raw, dimensions, device, _marker: PhantomData };
+        let raw_db = database.remap_types::<Bytes, Bytes>();
+        let mut stones = Vec::new();
+        for kv in raw_db.prefix_iter(wtxn, &index.to_be_bytes())? {
+            let (k, v) = kv?;
+            match k[2] {
+                3 => check(unsafe { ffi::hb_index_push_kv(this.raw, k.as_ptr(), k.len(), v.as_ptr(), v.len()) }, (0, 0))?, // Item nodes
+                1 => stones.push(k.to_vec()),                                                                          // Updated
+                _ => {}
+            }
+        }
+        let opts = ffi::hb_build_opts { m, m0, ef_construction, alpha, seed, batch_max: 0, dimensions: dimensions as u32 };
+        check(unsafe { ffi::hb_index_build_graph(this.raw, &opts, device, std::ptr::null_mut()) }, (0, 0))?;
+        extern "C" fn collect(user: *mut std::os::raw::c_void, k: *const u8, kl: usize, v: *const u8, vl: usize) -> i32 {
+            let out = unsafe { &mut *(user as *mut Vec<(Vec<u8>, Vec<u8>)>) };
+            out.push(unsafe { (std::slice::from_raw_parts(k, kl).to_vec(), std::slice::from_raw_parts(v, vl).to_vec()) });
+            0
+        }
+        let mut pairs: Vec<(Vec<u8>, Vec<u8>)> = Vec::new();
+        check(unsafe { ffi::hb_index_export_kv(this.raw, 0, collect, &mut pairs as *mut _ as *mut _) }, (0, 0))?;
+        for (k, v) in &pairs {
+            raw_db.put(wtxn, k, v)?;
+        }
+        for k in &stones {
+            raw_db.delete(wtxn, k)?;
+        }
+        check(unsafe { ffi::hb_index_finalize(this.raw, device) }, (0, 0))?;
+        Ok(this)
+    }
+
     pub fn dimensions(&self) -> usize {
         self.dimensions
     }

@@ -113,3 +113,57 @@ def test_build_small_and_degenerate_indexes():
         assert sorted(full[0][0, :full[2][0]].tolist()) == list(range(n))           # everything reachable with ef = n (reader.rs:80-110)
     rd = hb.Reader.build("cosine", 8, np.zeros(0, np.uint32), np.zeros((0, 8), np.float32), None)
     assert rd.n_items() == 0 and rd.nns(5).by_vectors_raw(np.ones((2, 8), np.float32))[2].tolist() == [0, 0]
+
+
+def test_build_from_the_writers_items_and_write_the_links_back():
+    """The integration path: the database holds what `Writer::add_item` left (Item nodes, metadata without a graph, the
+    `Updated` stones that make Reader::open fail with NeedBuild); the items are snapshotted through push_kv, the graph is
+    built on the device, and the Links / metadata pairs to `put` back are exported.  The CPU reader then opens them."""
+    import ctypes as C
+    from hannoy_b200 import _lib as L
+    n, dims, metric = 4000, 48, "euclidean"
+    ids = np.sort(np.random.default_rng(3).choice(1 << 20, n, replace=False)).astype(np.uint32)
+    src, x = make_db(metric, n, dims, seed=9, kind="clustered", ids=ids, build=True)
+    lib = L.lib()
+    pairs = [(bytes(k), bytes(v)) for k, v in src.export_kv(2)]
+    items_only = [(k, v) for k, v in pairs if k[2] == 3 or (k[2] == 0)]            # Item nodes + metadata/version
+    items_only += [(bytes([0, 2, 1]) + int(i).to_bytes(4, "big") + b"\0", b"") for i in ids[:5]]   # Updated stones (update_status.rs)
+    h = C.c_void_p()
+    assert lib.hb_index_begin(0, 2, C.byref(h)) == L.HB_OK
+    for k, v in items_only:
+        assert lib.hb_index_push_kv(h, k, len(k), v, len(v)) == L.HB_OK, lib.hb_last_error()
+    opts = L.BuildOpts(16, 32, 100, 1.0, 11, 0, 0)
+    st = np.zeros(8, np.uint64)
+    assert lib.hb_index_build_graph(h, C.byref(opts), 0, st.ctypes.data_as(C.c_void_p)) == L.HB_OK, lib.hb_last_error()
+    # a database that was never built: no metadata pair at all, the dimensions come from the caller
+    h2 = C.c_void_p()
+    assert lib.hb_index_begin(0, 2, C.byref(h2)) == L.HB_OK
+    for k, v in pairs:
+        if k[2] == 3:
+            assert lib.hb_index_push_kv(h2, k, len(k), v, len(v)) == L.HB_OK
+    assert lib.hb_index_build_graph(h2, C.byref(opts), 0, None) == L.HB_EMISSING_METADATA
+    opts2 = L.BuildOpts(16, 32, 100, 1.0, 11, 0, dims)
+    assert lib.hb_index_build_graph(h2, C.byref(opts2), 0, None) == L.HB_OK, lib.hb_last_error()
+    assert lib.hb_index_finalize(h2, 0) == L.HB_OK
+    rd2 = hb.Reader(h2, hb.Euclidean, 2, 0)
+    assert rd2.n_items() == n and rd2.dimensions() == dims
+    assert int(st[2]) == n
+    assert lib.hb_index_finalize(h, 0) == L.HB_OK, lib.hb_last_error()
+    rd = hb.Reader(h, hb.Euclidean, 2, 0)
+    kv = rd.export_kv(with_items=False)
+    meta, links, n_item_nodes = _decode(kv, 2)
+    assert n_item_nodes == 0 and np.array_equal(meta["items"], ids) and len(links) >= n
+    cpu = OracleDb(metric, dims)
+    cpu.add_items(ids, x)
+    for (item, layer), nb in links.items():
+        cpu.set_links(item, layer, nb)
+    cpu.set_entry_points(meta["eps"], meta["max_level"])
+    q = make_vectors(200, dims, seed=4, kind="clustered")
+    want = cpu.search_by_vector(q, 10, ef=64, counters=True, n_threads=4)
+    got = rd.nns(10).ef_search(64).by_vectors_raw(q, counters=True)
+    assert_same(got, want, "built from pushed items")
+    assert np.array_equal(got[3][:, :6], want[3][:, :6])
+    gt, _ = hb.exact_knn(rd, q, 10)
+    assert _recall(got[0], got[2], gt) > 0.8
+    g2 = rd2.nns(10).ef_search(64).by_vectors_raw(q)
+    assert_same(g2, got, "same seed, same items: the device build is deterministic")

@@ -1,4 +1,7 @@
-"""dev: recall of device-built vs CPU-built graphs for several batch limits (GPU box)."""
+"""Dev tool (GPU box): recall of device-built vs CPU-built graphs, per metric, with the build statistics.
+
+  python tools/build_quality.py [more]
+"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
