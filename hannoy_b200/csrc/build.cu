@@ -124,9 +124,6 @@ __device__ int robust_prune_warp(const DevIndex& ix, const unsigned long long* k
                                  float* sel_dist) {
     int n_sel = 0;
     __syncwarp();
-#ifdef HB_BUILD_DEBUG
-    if (n_c > 4096 || cap > 32) { if (lane_id() == 0) printf("[build] prune with n_c %d cap %d\n", n_c, cap); return 0; }
-#endif
     for (int i = 0; i < n_c && n_sel < cap; ++i) {
         const unsigned long long k = keys[i];
         const uint32_t cslot = (uint32_t)k, dq_bits = (uint32_t)(k >> 32);
@@ -146,20 +143,13 @@ __device__ int robust_prune_warp(const DevIndex& ix, const unsigned long long* k
 
 // Loads / stores of the mutable graph are strong (gpu scope) and carry a "memory" clobber, so neither the compiler nor
 // the L1 serves them from an earlier state.
-#ifdef HB_BUILD_ATOMIC_LISTS
-__device__ __forceinline__ uint32_t ld_cg(const uint32_t* p) { return atomicOr(const_cast<uint32_t*>(p), 0u); }
-__device__ __forceinline__ float ld_cg(const float* p) { return __uint_as_float(atomicOr(reinterpret_cast<uint32_t*>(const_cast<float*>(p)), 0u)); }
-__device__ __forceinline__ void st_cg(uint32_t* p, uint32_t v) { atomicExch(p, v); }
-__device__ __forceinline__ void st_cg(float* p, float v) { atomicExch(p, v); }
-#else
 __device__ __forceinline__ uint32_t ld_cg(const uint32_t* p) { uint32_t v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ float ld_cg(const float* p) { float v; asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_cg(uint32_t* p, uint32_t v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void st_cg(float* p, float v) { asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
-#endif
 
 // add_link (hnsw.rs:524-562) for node p on `level`; exactly one warp works on p at a time.  scratch: per-warp shared memory.
-__device__ void add_link_locked(const PruneLinkParams& P, uint32_t p, uint32_t x, float dist, unsigned long long* skeys, uint32_t* s_slot,
+__device__ void add_link_node(const PruneLinkParams& P, uint32_t p, uint32_t x, float dist, unsigned long long* skeys, uint32_t* s_slot,
                                 float* s_dist) {
     if (p == x) return;
     const int lane = lane_id();
@@ -170,11 +160,6 @@ __device__ void add_link_locked(const PruneLinkParams& P, uint32_t p, uint32_t x
     if (deg > cap || p >= P.ix.n || x >= P.ix.n) { build_fail(2, p, x, deg, lvl); return; }
     if (deg < cap) {
         if (lane == 0) { st_cg(&nb[deg], x); st_cg(&nd[deg], dist); st_cg(&P.g.deg[lvl][p], deg + 1); }
-#ifdef HB_BUILD_DEBUG
-        __syncwarp();
-        __threadfence();
-        { uint32_t e = lane <= (int)deg ? ld_cg(&nb[lane]) : 0; if (lane <= (int)deg && e >= P.ix.n) printf("[build] after append: p %u lvl %u deg %u -> %u, entry %d = %x (x = %u)\n", p, lvl, deg, deg + 1, lane, e, x); }
-#endif
         return;
     }
     // full: robust_prune(links) replaces the list, the new link is not part of it.  The <= 32 links are sorted by
@@ -199,10 +184,6 @@ __device__ void add_link_locked(const PruneLinkParams& P, uint32_t p, uint32_t x
     }
     if (lane == 0) st_cg(&P.g.deg[lvl][p], (uint32_t)n_sel);
     __syncwarp();
-#ifdef HB_BUILD_DEBUG
-    __threadfence();
-    { uint32_t e = lane < n_sel ? ld_cg(&nb[lane]) : 0; if (lane < n_sel && e >= P.ix.n) printf("[build] after rewrite: p %u lvl %u deg %u -> %d, entry %d = %x\n", p, lvl, deg, n_sel, lane, e); }
-#endif
 }
 
 constexpr int PL_WARPS = 4;
@@ -223,7 +204,7 @@ __global__ void __launch_bounds__(PL_WARPS * 32) prune_link_kernel(const PruneLi
     __syncwarp();
     P.sel_out[(size_t)i * 32 + lane] = lane < n_sel ? sel_slot[lane] : 0xffffffffu;   // eps.push(n), hnsw.rs:323
     // add_link(query, (dist, n)) for every selected n — hnsw.rs:320.  q is not linked yet: its list is this warp's alone.
-    for (int j = 0; j < n_sel; ++j) add_link_locked(P, q, sel_slot[j], sel_dist[j], sh_keys[wib], sh_slot[wib][1], sh_dist[wib][1]);
+    for (int j = 0; j < n_sel; ++j) add_link_node(P, q, sel_slot[j], sel_dist[j], sh_keys[wib], sh_slot[wib][1], sh_dist[wib][1]);
     // add_link(n, (dist, query)) — hnsw.rs:321 — is posted to n's inbox
     if (lane < n_sel) {
         const uint32_t t = sel_slot[lane];
@@ -266,7 +247,7 @@ __global__ void __launch_bounds__(PL_WARPS * 32) apply_reverse_kernel(const Prun
         __syncwarp();
         for (uint32_t j = 0; j < cnt; ++j) {
             const unsigned long long r = sh_in[wib][j];
-            add_link_locked(P, t, (uint32_t)r, __uint_as_float((uint32_t)(r >> 32)), sh_keys[wib], sh_slot[wib], sh_dist[wib]);
+            add_link_node(P, t, (uint32_t)r, __uint_as_float((uint32_t)(r >> 32)), sh_keys[wib], sh_slot[wib], sh_dist[wib]);
             __syncwarp();
         }
         if (lane == 0) P.g.inbox_cnt[t] = 0;
