@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <numeric>
 
 #include "dist.cuh"
@@ -80,41 +81,75 @@ struct PruneLinkParams {
     uint32_t* sel_out = nullptr;       // [n_items][32]: the selected neighbours = entry points of the next layer down (hnsw.rs:323)
 };
 
-// D::distance between two stored items, by the whole warp (any row kind; not the reference's summation order — the
-// builder has no bit-parity contract, only the reader has).
-__device__ float warp_pair_distance(const DevIndex& ix, uint32_t a, uint32_t b) {
+// D::distance between stored items, by the whole warp (any row kind; not the reference's summation order — the builder has
+// no bit-parity contract, only the reader has).
+// Distances from item `a` to up to PR_GROUP other items at once: the loads of all rows are in flight together, so a
+// candidate costs one memory round trip per PR_GROUP selected points instead of one per point.
+constexpr int PR_GROUP = 4;
+__device__ void warp_pair_distance_group(const DevIndex& ix, uint32_t a, const uint32_t* others, int g, float (&out)[PR_GROUP]) {
     const int lane = lane_id();
-    if (a >= ix.n || b >= ix.n) { build_fail(1, a, b, 0, 0); return 0.0f; }
+    uint32_t b[PR_GROUP];
+#pragma unroll
+    for (int r = 0; r < PR_GROUP; ++r) b[r] = others[r < g ? r : 0];
+    bool bad = a >= ix.n;
+#pragma unroll
+    for (int r = 0; r < PR_GROUP; ++r) bad = bad || b[r] >= ix.n;
+    if (bad) {
+        build_fail(1, a, b[0], (unsigned)g, 0);
+#pragma unroll
+        for (int r = 0; r < PR_GROUP; ++r) out[r] = 0.0f;
+        return;
+    }
     const uint8_t* ra = ix.rows + (size_t)a * ix.row_stride;
-    const uint8_t* rb = ix.rows + (size_t)b * ix.row_stride;
+    const uint8_t* rb[PR_GROUP];
+#pragma unroll
+    for (int r = 0; r < PR_GROUP; ++r) rb[r] = ix.rows + (size_t)b[r] * ix.row_stride;
     const uint32_t words = ix.row_stride / 16;
     if (ix.kind == KIND_BIN) {
-        uint32_t h = 0;
+        uint32_t h[PR_GROUP] = {};
         for (uint32_t w = lane; w < words; w += 32) {
-            ulonglong2 x = __ldg(reinterpret_cast<const ulonglong2*>(ra) + w), y = __ldg(reinterpret_cast<const ulonglong2*>(rb) + w);
-            h += __popcll(x.x ^ y.x) + __popcll(x.y ^ y.y);
+            const ulonglong2 x = __ldg(reinterpret_cast<const ulonglong2*>(ra) + w);
+            ulonglong2 y[PR_GROUP];
+#pragma unroll
+            for (int r = 0; r < PR_GROUP; ++r) y[r] = __ldg(reinterpret_cast<const ulonglong2*>(rb[r]) + w);
+#pragma unroll
+            for (int r = 0; r < PR_GROUP; ++r) h[r] += __popcll(x.x ^ y[r].x) + __popcll(x.y ^ y[r].y);
         }
         __syncwarp();
-        h = __reduce_add_sync(FULL, h);
-        const float na = ix.metric == HB_BQ_COSINE ? __ldg(&ix.hdr[a]) : 0.0f, nb = ix.metric == HB_BQ_COSINE ? __ldg(&ix.hdr[b]) : 0.0f;
-        return finish_bin(ix.metric, h, ix.n_words * 64u, na, nb);
+        const float na = ix.metric == HB_BQ_COSINE ? __ldg(&ix.hdr[a]) : 0.0f;
+#pragma unroll
+        for (int r = 0; r < PR_GROUP; ++r) {
+            const uint32_t hr = __reduce_add_sync(FULL, h[r]);
+            out[r] = finish_bin(ix.metric, hr, ix.n_words * 64u, na, ix.metric == HB_BQ_COSINE ? __ldg(&ix.hdr[b[r]]) : 0.0f);
+        }
+        return;
     }
-    float acc = 0.0f;
+    float acc[PR_GROUP] = {};
     for (uint32_t w = lane; w < words; w += 32) {
-        float4 x = __ldg(reinterpret_cast<const float4*>(ra) + w), y = __ldg(reinterpret_cast<const float4*>(rb) + w);
-        if (ix.metric == HB_COSINE) {
-            acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
-        } else if (ix.metric == HB_MANHATTAN) {
-            acc += fabsf(x.x - y.x) + fabsf(x.y - y.y) + fabsf(x.z - y.z) + fabsf(x.w - y.w);
-        } else {
-            float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
-            acc = fmaf(d0, d0, acc); acc = fmaf(d1, d1, acc); acc = fmaf(d2, d2, acc); acc = fmaf(d3, d3, acc);
+        const float4 x = __ldg(reinterpret_cast<const float4*>(ra) + w);
+        float4 y[PR_GROUP];
+#pragma unroll
+        for (int r = 0; r < PR_GROUP; ++r) y[r] = __ldg(reinterpret_cast<const float4*>(rb[r]) + w);
+#pragma unroll
+        for (int r = 0; r < PR_GROUP; ++r) {
+            if (ix.metric == HB_COSINE) {
+                acc[r] = fmaf(x.x, y[r].x, acc[r]); acc[r] = fmaf(x.y, y[r].y, acc[r]); acc[r] = fmaf(x.z, y[r].z, acc[r]); acc[r] = fmaf(x.w, y[r].w, acc[r]);
+            } else if (ix.metric == HB_MANHATTAN) {
+                acc[r] += fabsf(x.x - y[r].x) + fabsf(x.y - y[r].y) + fabsf(x.z - y[r].z) + fabsf(x.w - y[r].w);
+            } else {
+                const float d0 = x.x - y[r].x, d1 = x.y - y[r].y, d2 = x.z - y[r].z, d3 = x.w - y[r].w;
+                acc[r] = fmaf(d0, d0, acc[r]); acc[r] = fmaf(d1, d1, acc[r]); acc[r] = fmaf(d2, d2, acc[r]); acc[r] = fmaf(d3, d3, acc[r]);
+            }
         }
     }
     __syncwarp();  // lanes leave the strided loop at different trip counts
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-    if (ix.metric == HB_COSINE) return finish_f32(HB_COSINE, acc, __ldg(&ix.hdr[a]), __ldg(&ix.hdr[b]));
-    return acc;
+    const float na = ix.metric == HB_COSINE ? __ldg(&ix.hdr[a]) : 0.0f;
+#pragma unroll
+    for (int r = 0; r < PR_GROUP; ++r) {
+        float v = acc[r];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        out[r] = ix.metric == HB_COSINE ? finish_f32(HB_COSINE, v, na, __ldg(&ix.hdr[b[r]])) : v;
+    }
 }
 
 // robust_prune (hnsw.rs:567-597): candidates in ascending (distance bits, slot) order in keys[0..n_c); selects at most
@@ -128,9 +163,13 @@ __device__ int robust_prune_warp(const DevIndex& ix, const unsigned long long* k
         const unsigned long long k = keys[i];
         const uint32_t cslot = (uint32_t)k, dq_bits = (uint32_t)(k >> 32);
         bool ok = true;
-        for (int j = 0; j < n_sel; ++j) {
-            const float d = warp_pair_distance(ix, cslot, sel_slot[j]);
-            if (__float_as_uint(d * alpha) < dq_bits) { ok = false; break; }   // OrderedFloat(d * alpha) < dist_to_query
+        for (int j0 = 0; j0 < n_sel && ok; j0 += PR_GROUP) {
+            const int g = min(PR_GROUP, n_sel - j0);
+            float d[PR_GROUP];
+            warp_pair_distance_group(ix, cslot, sel_slot + j0, g, d);
+#pragma unroll
+            for (int r = 0; r < PR_GROUP; ++r)
+                if (r < g && __float_as_uint(d[r] * alpha) < dq_bits) ok = false;   // OrderedFloat(d * alpha) < dist_to_query
         }
         if (ok) {
             if (lane_id() == 0) { sel_slot[n_sel] = cslot; sel_dist[n_sel] = __uint_as_float(dq_bits); }
@@ -294,6 +333,8 @@ struct Frees {
 // HnswBuilder::build for every item of `ix` (hnsw.rs:122-216): fills ix->layers / eps / max_level on the host.
 hb_status build_graph_on_device(hb_index* ix, uint32_t M, uint32_t M0, uint32_t efc, float alpha, uint64_t seed, uint32_t batch_max, int device,
                                 uint64_t* stats /* [8]: batches, launches, items, max_level, reverse links dropped (inbox full), walks cut short */) {
+    const auto t_start = std::chrono::steady_clock::now();
+    auto ms_since = [](std::chrono::steady_clock::time_point t0) { return (uint64_t)std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count(); };
     const size_t n = ix->ids.size();
     if (M < 2 || M > 32 || M0 < 2 || M0 > FIXED_DEG || efc < 1 || efc > 4096) { set_error("hb_index_build_graph: need 2 <= M <= 32, 2 <= M0 <= 32, 1 <= ef_construction <= 4096"); return HB_EINVAL; }
     if (n >= 0xfffffff0ull / 32) { set_error("too many items"); return HB_EINVAL; }
@@ -436,6 +477,7 @@ hb_status build_graph_on_device(hb_index* ix, uint32_t M, uint32_t M0, uint32_t 
         CUDA_TRYB(cudaMemcpyToSymbol(g_build_err, zero, sizeof(zero)));
     }
     uint64_t n_batches = 0, n_launch = 0;
+    const auto t_loop = std::chrono::steady_clock::now();
     const size_t inflight_div = (size_t)std::max(1, tunable("build_inflight_div", 64));
     const bool sync_each = tunable("build_sync", 0) != 0;
     const int link_blocks = tunable("build_link_blocks", 0);  // debugging aid: cap the prune/link grid  // debugging aid: a failure is reported with the launch that caused it
@@ -500,6 +542,7 @@ hb_status build_graph_on_device(hb_index* ix, uint32_t M, uint32_t M0, uint32_t 
         }
     }
     CUDA_TRYB(cudaDeviceSynchronize());
+    const uint64_t loop_ms = ms_since(t_loop);
 
     // ---- back to the host: per-layer CSR over slots, neighbours ascending (what Links / roaring iteration give the reader) ----
     ix->layers.assign(L + 1, HostLayer());
@@ -533,6 +576,7 @@ hb_status build_graph_on_device(hb_index* ix, uint32_t M, uint32_t M0, uint32_t 
         unsigned long long h[2] = {};
         CUDA_TRYB(cudaMemcpy(h, g.n_dropped, 16, cudaMemcpyDeviceToHost));
         stats[0] = n_batches; stats[1] = n_launch; stats[2] = n; stats[3] = L; stats[4] = h[0]; stats[5] = h[1];
+        stats[6] = loop_ms; stats[7] = ms_since(t_start);
     }
     return HB_OK;
 }

@@ -364,7 +364,7 @@ class Reader:
             st = np.zeros(8, np.uint64)
             _check(lib.hb_index_build_graph(h, C.byref(o), device, _ptr(st)))
             if stats is not None:
-                stats.update(batches=int(st[0]), launches=int(st[1]), items=int(st[2]), max_level=int(st[3]), dropped=int(st[4]), cut=int(st[5]))
+                stats.update(batches=int(st[0]), launches=int(st[1]), items=int(st[2]), max_level=int(st[3]), dropped=int(st[4]), cut=int(st[5]), kernels_ms=int(st[6]), build_call_ms=int(st[7]))
             _check(lib.hb_index_finalize(h, device))
         except Exception:
             lib.hb_index_free(h)

@@ -103,7 +103,8 @@ hb_status hb_index_load(hb_index*, const char* path);
  * reference's on-disk encoding.  Like the reference's rayon build the result depends on insertion interleaving: a
  * valid hannoy graph of the same quality, not a bit-copy of a CPU build.  M <= 32, M0 <= 32.
  * stats_out (optional): u64[8] = batches, kernel launches, items, max_level, reverse links dropped because more than 32
- * arrived for one node in one batch, candidate walks cut short, 0, 0. */
+ * arrived for one node in one batch, candidate walks cut short, milliseconds in the batch loop (kernels), milliseconds in
+ * the whole call (row upload, kernels, download and CSR). */
 typedef struct {
     uint32_t M, M0;            /* HannoyBuilder::<M, M0> const generics, 16 / 32 in the reference's docs and benches */
     uint32_t ef_construction;  /* HannoyBuilder::ef_construction, default 100 (writer.rs) */
