@@ -8,6 +8,11 @@
 #include <cctype>
 #include <cstring>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "common.h"
 
 namespace hb {
@@ -236,20 +241,22 @@ hb_status hb_index_save(const hb_index* ix, const char* path) {
 hb_status hb_index_load(hb_index* ix, const char* path) {
     if (!ix || !path) { set_error("hb_index_load: null argument"); return HB_EINVAL; }
     if (ix->finalized || !ix->ids.empty() || ix->have_metadata) { set_error("hb_index_load: the index is not empty"); return HB_ESTATE; }
-    FILE* f = fopen(path, "rb");
-    if (!f) { set_error("snapshot: cannot open %s", path); return HB_EINVAL; }
+    // the file is mapped, not read: the arrays are copied once, straight into the snapshot
+    int fd = open(path, O_RDONLY | O_CLOEXEC);
+    if (fd < 0) { set_error("snapshot: cannot open %s", path); return HB_EINVAL; }
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || sb.st_size <= 0) { close(fd); set_error("snapshot: cannot stat %s", path); return HB_EFORMAT; }
+    void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m == MAP_FAILED) { close(fd); set_error("snapshot: mmap of %s failed", path); return HB_ENOMEM; }
+    madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
     hb_status st = HB_OK;
     try {
-        fseek(f, 0, SEEK_END);
-        long sz = ftell(f);
-        fseek(f, 0, SEEK_SET);
-        std::vector<uint8_t> buf(sz > 0 ? (size_t)sz : 0);
-        if (!buf.empty() && fread(buf.data(), 1, buf.size(), f) != buf.size()) { set_error("snapshot: short read on %s", path); st = HB_EINVAL; }
-        if (st == HB_OK) st = snapshot_load(ix, buf.data(), buf.size());
+        st = snapshot_load(ix, (const uint8_t*)m, (size_t)sb.st_size);
     } catch (const std::bad_alloc&) {
         st = HB_ENOMEM;
     }
-    fclose(f);
+    munmap(m, (size_t)sb.st_size);
+    close(fd);
     return st;
 }
 

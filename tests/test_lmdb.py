@@ -309,3 +309,32 @@ def test_snapshot_file_search_equals_oracle(tmp_path):
         assert np.array_equal(got[3][:, :6], want[3][:, :6])
     with pytest.raises(hb.UnmatchingDistance):
         hb.Reader.load(str(tmp_path / "c.hb"), 0, hb.Euclidean)
+
+
+# ---- randomized trees (hypothesis) ------------------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as hst
+
+
+@settings(max_examples=40, deadline=None)
+@given(n=hst.integers(0, 1500), psize=hst.sampled_from([512, 1024, 4096, 8192, 65536]), fill=hst.floats(0.3, 1.0),
+       big_every=hst.integers(0, 12), klen=hst.integers(1, 24), named=hst.booleans(), newest=hst.integers(0, 1), seed=hst.integers(0, 1 << 30),
+       prefix_len=hst.integers(0, 3))
+def test_scan_randomized_trees(tmp_path_factory, n, psize, fill, big_every, klen, named, newest, seed, prefix_len):
+    """Any key length, page size, fill factor, overflow density, database naming and meta-page order: a prefix scan returns
+    exactly the pairs whose key starts with the prefix, in key order."""
+    pairs = _random_pairs(n, seed=seed, big_every=big_every, klen=klen)
+    # keys longer than what fits a branch page next to another key are not valid LMDB keys (mdb_env_get_maxkeysize ~ psize / 8)
+    if klen > psize // 8:
+        return
+    w = LmdbWriter(psize=psize, fill=fill)
+    if named:
+        w.put_named("db", pairs)
+    else:
+        w.put_unnamed(pairs)
+    d = tmp_path_factory.mktemp("env")
+    w.save(str(d), txnid=5, newest_meta=newest)
+    prefix = pairs[len(pairs) // 2][0][:prefix_len] if pairs else b"\x01\x02\x03"[:prefix_len]
+    st, got, txn = _scan(str(d), "db" if named else None, prefix)
+    assert st == L.HB_OK, L.lib().hb_last_error()
+    assert txn == 5
+    assert got == [p for p in pairs if p[0].startswith(prefix)]
