@@ -59,7 +59,7 @@ def main():
     gt, _ = hb.exact_knn(rd, q_host[:n_gt], k)
     log(f"exact k-NN (quantized metric) for {n_gt} queries in {time.time() - t:.1f}s")
     sweep, ef_pick = {}, None
-    for ef in (100, 200, 400):
+    for ef in (100, 200, 400, 800):
         ids, dd, lens = rd.nns(k).ef_search(ef).by_vectors_raw(q_host[:n_gt])
         sweep[ef] = round(bench.recall_at_k(ids, lens, gt, k), 4)
         if ef_pick is None and sweep[ef] >= 0.95:
