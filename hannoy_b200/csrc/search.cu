@@ -103,81 +103,17 @@ __device__ __forceinline__ bool cancel_poll(Ctx& c) {
     return (c.p.cancel_after && c.polls >= c.p.cancel_after) || cancel_flag_set(c);
 }
 
-// ---- one-by-one heap updates: the fallback for heaps of more than 32 * MERGE_TILES entries (large ef, pass 1) ----
-// Kept out of line (cold): it works on a copy of the heap state so that Ctx never has its address taken.
-struct Heaps {
-    u64* res; int res_len, res_cap;
-    u64* que; int q_len, q_cap;
-    int pass; bool overflow;  // pass != 0: never prune (also set for the poll-exact cancellation mode)
-};
-// res.push (unconditional)
-__device__ __forceinline__ void res_push(Heaps& c, u64 key) {
-    if (c.res_len >= c.res_cap) { c.overflow = true; return; }
-    int pos = count_lt(c.res, c.res_len, key);
-    insert_at(c.res, c.res_len, pos, key);
-    c.res_len++;
-}
-// `if res.len() == ef { push_pop_max } else { push }` — reader.rs:360-364
-__device__ __forceinline__ void res_accept(Heaps& c, u64 key, int ef) {
-    if (c.res_len == ef) {
-        if (ef == 0) return;                      // push_pop_max on an empty heap returns the item
-        if (key > c.res[c.res_len - 1]) return;   // pushed and popped straight away
-        int pos = count_lt(c.res, c.res_len - 1, key);
-        insert_at(c.res, c.res_len - 1, pos, key);
-    } else {
-        res_push(c, key);
-    }
-}
-// An entry can never be popped again once res is full and its distance exceeds the current f_max:
-// f_max never grows while res.len() >= ef, and the loop breaks at the first `f > f_max`
-// (reader.rs:333-336).  Only argued for non-negative distances (bit order == numeric order).
+// An entry of the search queue can never be popped again once the result set is full and its distance exceeds the
+// current f_max: f_max never grows while res.len() >= ef, and the loop breaks at the first `f > f_max`
+// (reader.rs:333-336).  Such dead entries are trimmed from the queue (heaps_stage_queue).  Only argued for non-negative
+// distances (bit order == numeric order).
 //
-// Pruned entries are also the reference's "break sentinels": popping one ends the walk before any entry
-// that follows it in BIT order.  For non-negative distances every follower would end the walk itself, so
-// dropping the sentinel changes nothing; a negative distance (only BinaryQuantizedCosine can produce one,
-// binary_quantized_cosine.rs:49-58 has no clamp) sorts last by bits yet passes `f > f_max`, so the first
-// negative distance seen in the pruning pass sends the query to pass 1, which never prunes.
-__device__ __forceinline__ bool is_dead(const Heaps& c, uint32_t bits, int ef) {
-    if (c.pass != 0) return false;
-    if (c.res_len < ef || c.res_len == 0) return false;
-    uint32_t mb = (uint32_t)(c.res[c.res_len - 1] >> 32);
-    if ((bits | mb) & 0x80000000u) return false;
-    return __uint_as_float(bits) > __uint_as_float(mb);
-}
-// search_queue.push — reader.rs:319,354
-__device__ __forceinline__ void queue_push(Heaps& c, uint32_t bits, uint32_t slot, int ef) {
-    if (is_dead(c, bits, ef)) return;
-    u64 qk = ((u64)bits << 32) | (uint32_t)(~slot);
-    if (c.q_len == c.q_cap) {
-        u64 worst = c.que[0];
-        if (qk > worst) { c.overflow = true; return; }  // would have to drop a live entry
-        if (!is_dead(c, (uint32_t)(worst >> 32), ef)) c.overflow = true;
-        int pos = count_gt(c.que, c.q_len, qk);
-        insert_drop_front(c.que, pos, qk);
-    } else {
-        int pos = count_gt(c.que, c.q_len, qk);
-        insert_at(c.que, c.q_len, pos, qk);
-        c.q_len++;
-    }
-}
+// Dead entries are also the reference's "break sentinels": popping one ends the walk before any entry that follows it
+// in BIT order.  For non-negative distances every follower would end the walk itself, so dropping the sentinel changes
+// nothing; a negative distance (only BinaryQuantizedCosine can produce one, binary_quantized_cosine.rs:49-58 has no
+// clamp) sorts last by bits yet passes `f > f_max`, so the first negative distance seen in the trimming pass sends the
+// query to pass 1, which never trims.
 enum ChunkMode { CH_EP, CH_NBR, CH_LINEAR };
-__device__ __noinline__ void heaps_update_seq(Heaps* hp, int mode, int ef, unsigned resm, unsigned accm, uint32_t bits, uint32_t s) {
-    Heaps h = *hp;
-    const u64 key = ((u64)bits << 32) | s;
-    for (unsigned m = resm; m; m &= m - 1) {
-        u64 k = __shfl_sync(FULL, key, __ffs(m) - 1);
-        if (mode == CH_EP) res_push(h, k);       // reader.rs:322-324: unconditional
-        else res_accept(h, k, ef);
-    }
-    if (mode != CH_LINEAR) {
-        for (unsigned m = accm; m; m &= m - 1) {
-            int src = __ffs(m) - 1;
-            uint32_t b = __shfl_sync(FULL, bits, src), sl = __shfl_sync(FULL, s, src);
-            queue_push(h, b, sl, ef);
-        }
-    }
-    *hp = h;
-}
 
 // ---- visited set --------------------------------------------------------------------------------------
 // `path.insert(point)` in two halves so that independent work can sit between the atomic and its use:
@@ -332,7 +268,7 @@ __device__ __forceinline__ float rows_finish(Ctx& c, const RowsInFlight& rf, uin
     return mine;
 }
 
-constexpr int MERGE_TILES = 8;  // heaps of up to 256 entries are updated by one merge pass per chunk
+constexpr int MERGE_TILES = 8;  // heaps of up to 256 entries are merged through registers, larger ones tile by tile in place
 
 __device__ __forceinline__ u64 warp_min_u64(u64 v) {
     uint32_t hi = (uint32_t)(v >> 32);
@@ -359,22 +295,12 @@ struct ChunkUpdate {
 __device__ __forceinline__ void heaps_stage_res(Ctx& c, ChunkUpdate& u, int ef) {
     const unsigned resm = __ballot_sync(FULL, u.acc && u.pf);
     u.seq_done = false;
-    if (c.res_len <= 32 * MERGE_TILES && c.q_len <= 32 * MERGE_TILES) {
-        // Pushing the keys one by one with `if len == ef { push_pop_max } else { push }` leaves the min(ef, len + m)
-        // smallest of the union when len <= ef, and the whole union when len > ef (or for entry points).
-        const int m_res = __popc(resm);
-        int target = (u.mode == CH_EP || c.res_len > ef) ? c.res_len + m_res : min(ef, c.res_len + m_res);
-        if (target > c.res_cap) { c.overflow = true; return; }
-        if (m_res) c.res_len = merge_batch<false, false, MERGE_TILES>(c.res, c.res_len, u.acc && u.pf, ((u64)u.bits << 32) | u.s, target, 0u);
-    } else {
-        const unsigned accm = __ballot_sync(FULL, u.acc && !u.qskip);
-        Heaps h{c.res, c.res_len, c.res_cap, c.que, c.q_len, c.q_cap, c.p.pass | (int)c.p.cancel_after | c.p.no_trim, false};
-        heaps_update_seq(&h, u.mode, ef, resm, accm, u.bits, u.s);
-        c.res_len = h.res_len;
-        c.q_len = h.q_len;
-        if (h.overflow) c.overflow = true;
-        u.seq_done = true;
-    }
+    // Pushing the keys one by one with `if len == ef { push_pop_max } else { push }` leaves the min(ef, len + m)
+    // smallest of the union when len <= ef, and the whole union when len > ef (or for entry points).
+    const int m_res = __popc(resm);
+    int target = (u.mode == CH_EP || c.res_len > ef) ? c.res_len + m_res : min(ef, c.res_len + m_res);
+    if (target > c.res_cap) { c.overflow = true; return; }
+    if (m_res) c.res_len = merge_any<false, false, MERGE_TILES>(c.res, c.res_len, u.acc && u.pf, ((u64)u.bits << 32) | u.s, target, 0u);
 }
 __device__ __forceinline__ void heaps_stage_queue(Ctx& c, const ChunkUpdate& u, int ef) {
     if (u.seq_done || u.mode == CH_LINEAR || c.overflow) return;
@@ -395,7 +321,7 @@ __device__ __forceinline__ void heaps_stage_queue(Ctx& c, const ChunkUpdate& u, 
     }
     // nothing to insert and no dead entry at the front (they form a prefix of the descending array): the queue is unchanged
     if (mq || (prune && c.q_len > 0 && (uint32_t)(c.que[0] >> 32) > mb))
-        c.q_len = merge_batch<true, true, MERGE_TILES>(c.que, c.q_len, qhas, ((u64)u.bits << 32) | (uint32_t)(~u.s), c.q_cap, mb);
+        c.q_len = merge_any<true, true, MERGE_TILES>(c.que, c.q_len, qhas, ((u64)u.bits << 32) | (uint32_t)(~u.s), c.q_cap, mb);
 }
 
 // Visitor::visit — reader.rs:301-369 — and, with `linear`, the candidate loop of brute_force_search

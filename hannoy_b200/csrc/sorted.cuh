@@ -138,4 +138,69 @@ __device__ HB_MERGE_INLINE int merge_batch(u64* a, int len, bool has, u64 key, i
     return new_len;
 }
 
+// The same merge for arrays of any length (heaps beyond 32 * MAX_TILES entries: large ef, the global-memory pass): the
+// old entries are moved tile by tile from the top down, each by the number of new keys that sort before it; tiles below
+// the first insertion point are not touched.  A dead prefix (TRIM) is compacted away first, bottom up.
+template <bool DESC, bool TRIM>
+__device__ __noinline__ int merge_batch_large(u64* a, int len, bool has, u64 key, int keep, uint32_t drop_above) {
+    const int lane = lane_id();
+    if (TRIM && len > 0 && (uint32_t)(a[0] >> 32) > drop_above) {
+        int d = 0;
+        for (int i = lane; i < len; i += 32) d += (uint32_t)(a[i] >> 32) > drop_above;
+        d = __reduce_add_sync(FULL, d);
+        for (int base = d; base < len; base += 32) {  // a[i] -> a[i - d], bottom up
+            const int i = base + lane;
+            const u64 v = i < len ? a[i] : 0ull;
+            __syncwarp();
+            if (i < len) a[i - d] = v;
+            __syncwarp();
+        }
+        len -= d;
+    }
+    const unsigned hm = __ballot_sync(FULL, has);
+    if (!hm) return min(len, keep);
+    int pos = 0x7fffffff;
+    if (has) {
+        int lo = 0, hi = len;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const u64 x = a[mid];
+            const bool before = DESC ? (x > key) : (x < key);
+            if (before) lo = mid + 1; else hi = mid;
+        }
+        pos = lo;
+    }
+    const int t0 = (int)(__reduce_min_sync(FULL, (unsigned)pos) >> 5);
+    if (!has) pos = 0x7fffffff;
+    int rank = 0;
+    for (unsigned m = hm; m; m &= m - 1) {
+        const u64 kb = __shfl_sync(FULL, key, __ffs(m) - 1);
+        rank += DESC ? (kb > key) : (kb < key);
+    }
+    const int new_len = min(len + __popc(hm), keep);
+    __syncwarp();
+    for (int t = (len - 1) >> 5; t >= t0 && len > 0; --t) {
+        const int i = t * 32 + lane;
+        const u64 v = i < len ? a[i] : 0ull;
+        int sh = 0;
+        for (unsigned m = hm; m; m &= m - 1) sh += __shfl_sync(FULL, pos, __ffs(m) - 1) <= i;
+        __syncwarp();  // the tile is in registers: its cells (and the ones above, already moved) may be overwritten
+        if (i < len && i + sh < new_len) a[i + sh] = v;
+        __syncwarp();
+    }
+    if (has) {
+        const int j = pos + rank;
+        if (j < new_len) a[j] = key;
+    }
+    __syncwarp();
+    return new_len;
+}
+
+// merge of up to 32 keys into a sorted array of any length
+template <bool DESC, bool TRIM, int MAX_TILES>
+__device__ __forceinline__ int merge_any(u64* a, int len, bool has, u64 key, int keep, uint32_t drop_above) {
+    if (len <= 32 * MAX_TILES) return merge_batch<DESC, TRIM, MAX_TILES>(a, len, has, key, keep, drop_above);
+    return merge_batch_large<DESC, TRIM>(a, len, has, key, keep, drop_above);
+}
+
 }  // namespace hb

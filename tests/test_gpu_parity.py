@@ -168,3 +168,25 @@ def test_concurrent_calls_threads_and_streams():
         d_q, d_ids, d_dist, d_len = bufs[i]
         g = (d_ids.cpu().numpy().view(np.uint32), d_dist.cpu().numpy(), d_len.cpu().numpy().view(np.uint32))
         assert_same(g, want[i], f"stream {i}")
+
+
+@pytest.mark.parametrize("metric,n,dims,kind", [("cosine", 5000, 64, "clustered"), ("binary quantized cosine", 6000, 1024, "clustered"),
+                                                ("euclidean", 4000, 20, "uniform"), ("hamming", 4000, 128, "uniform")])
+def test_large_ef_heaps(metric, n, dims, kind):
+    """ef beyond 256 entries: the heaps are merged tile by tile in place (sorted.cuh merge_batch_large), still in shared
+    memory up to what fits, in global memory (pass 1) beyond — same ids, distance bits and traversal counters."""
+    db, x = make_db(metric, n, dims, seed=n + dims + 5, kind=kind, n_threads=4)
+    rd = open_reader_arrays(db, metric)
+    q = make_vectors(48, dims, seed=3, kind=kind)
+    for count, ef in [(100, 300), (100, 800), (10, 257), (300, 300), (50, 2000), (1000, 1000), (10, n)]:
+        want = db.search_by_vector(q, count, ef=max(ef, count), counters=True, n_threads=4)
+        got = rd.nns(count).ef_search(ef).by_vectors_raw(q, counters=True)
+        assert_same(got, want, f"{metric} k={count} ef={ef}")
+        assert_counters_same(got[3], want[3], f"{metric} k={count} ef={ef}")
+    cand = np.arange(0, n, 3, dtype=np.uint32)
+    want = db.search_by_vector(q, 100, ef=600, candidates=cand, linear_below=0, counters=True, n_threads=4)
+    got = rd.nns(100).ef_search(600).candidates(cand).linear_below(0).by_vectors_raw(q, counters=True)
+    assert_same(got, want, f"{metric} filtered, ef=600")
+    assert_counters_same(got[3], want[3], f"{metric} filtered, ef=600")
+    items = np.array([0, 11, n - 1], np.uint32)
+    assert_same(rd.nns(100).ef_search(700).by_items_raw(items), db.search_by_item(items, 100, ef=700), f"{metric} by_item ef=700")
