@@ -66,7 +66,7 @@ impl<D: Distance> GpuReader<D> {
         assert!(metric >= 0, "distance {:?} has no GPU kernel", D::name());
         let mut raw = std::ptr::null_mut();
         check(unsafe { ffi::hb_index_begin(metric, index, &mut raw) }, (0, 0))?;
-        let this = GpuReader { raw, dimensions: 0, device, _marker: PhantomData };
+        let mut this = GpuReader { raw, dimensions: 0, device, _marker: PhantomData };
         // every key of this index starts with its big-endian u16 (key.rs:54-66)
         let prefix = index.to_be_bytes();
         let raw_db = database.remap_types::<Bytes, Bytes>();
@@ -80,8 +80,8 @@ impl<D: Distance> GpuReader<D> {
             }
             st => check(st, (0, 0))?,
         }
-        let dimensions = unsafe { ffi::hb_index_dimensions(this.raw) } as usize;
-        Ok(GpuReader { dimensions, ..this })
+        this.dimensions = unsafe { ffi::hb_index_dimensions(this.raw) } as usize;
+        Ok(this) // (a struct update `..this` would move out of a Drop type)
     }
 
     /// `Reader::open` without heed: the library walks `<path>/data.mdb` itself (`db_name = None` is the unnamed
