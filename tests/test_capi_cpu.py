@@ -298,3 +298,28 @@ def test_export_kv_writes_the_reference_encoding(metric, dims, n, dense):
         lib.hb_index_free(e)
     lib.hb_index_free(g)
     lib.hb_index_free(h)
+
+
+# ---- hostile input never crashes the decoders ---------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as hst
+
+
+@settings(max_examples=300, deadline=None)
+@given(mode=hst.sampled_from([0, 1, 2, 3]), item=hst.integers(0, 3), layer=hst.integers(0, 3), val=hst.binary(min_size=0, max_size=96),
+       metric=hst.sampled_from([0, 1, 3, 4]))
+def test_push_kv_survives_arbitrary_values(mode, item, layer, val, metric):
+    """Any byte string as a value: HB_OK or HB_EFORMAT, never a fault (metadata / version / roaring / item decoders)."""
+    lib = L.lib()
+    h = _begin(metric, index=1)
+    key = bytes([0, 1, mode]) + item.to_bytes(4, "big") + bytes([layer])
+    st = lib.hb_index_push_kv(h, key, len(key), val, len(val))
+    assert st in (L.HB_OK, L.HB_EFORMAT), st
+    # a plausible roaring prefix followed by garbage exercises the container bounds checks
+    r = (12346).to_bytes(4, "little") + (3).to_bytes(4, "little") + val
+    st = lib.hb_index_push_kv(h, bytes([0, 1, 2, 0, 0, 0, 5, 0]), 8, b"\x01" + r, 1 + len(r))
+    assert st in (L.HB_OK, L.HB_EFORMAT)
+    r = (12347 | (2 << 16)).to_bytes(4, "little") + b"\x07" + val
+    st = lib.hb_index_push_kv(h, bytes([0, 1, 2, 0, 0, 0, 6, 0]), 8, b"\x01" + r, 1 + len(r))
+    assert st in (L.HB_OK, L.HB_EFORMAT)
+    assert lib.hb_index_finalize(h, 0) in (L.HB_OK, L.HB_ECUDA, L.HB_EFORMAT, L.HB_EMISSING_METADATA, L.HB_EUNMATCHING_DISTANCE, L.HB_ENEED_BUILD, L.HB_EINVAL)
+    lib.hb_index_free(h)

@@ -338,3 +338,29 @@ def test_scan_randomized_trees(tmp_path_factory, n, psize, fill, big_every, klen
     assert st == L.HB_OK, L.lib().hb_last_error()
     assert txn == 5
     assert got == [p for p in pairs if p[0].startswith(prefix)]
+
+
+@settings(max_examples=60, deadline=None)
+@given(seed=hst.integers(0, 1 << 30), n_flips=hst.integers(1, 40), region=hst.sampled_from(["meta", "any"]))
+def test_corrupted_data_files_never_fault(tmp_path_factory, seed, n_flips, region):
+    """Random byte damage anywhere in data.mdb (or concentrated in the meta pages): the walker answers with a status —
+    every page number, node offset and size is bounds-checked — and the index decoder behind it never faults either."""
+    rng = np.random.default_rng(seed)
+    db, _ = make_db("euclidean", 120, 24, seed=1)
+    d = tmp_path_factory.mktemp("env")
+    fn = _write_env(d, {3: db}, fill=0.8)
+    blob = bytearray(open(fn, "rb").read())
+    hi = 2 * 4096 if region == "meta" else len(blob)
+    for _ in range(n_flips):
+        blob[int(rng.integers(0, hi))] = int(rng.integers(0, 256))
+    open(fn, "wb").write(blob)
+    st, got, _ = _scan(fn)
+    assert st in (L.HB_OK, L.HB_EFORMAT, L.HB_EINVAL, L.HB_ESTATE)
+    lib = L.lib()
+    h = C.c_void_p()
+    assert lib.hb_index_begin(0, 3, C.byref(h)) == L.HB_OK
+    st = lib.hb_index_push_lmdb(h, os.fsencode(fn), None, None)
+    assert st in (L.HB_OK, L.HB_EFORMAT, L.HB_EINVAL, L.HB_ESTATE)
+    if st == L.HB_OK:
+        assert lib.hb_index_finalize(h, 0) in (L.HB_OK, L.HB_ECUDA, L.HB_EFORMAT, L.HB_EMISSING_METADATA, L.HB_EUNMATCHING_DISTANCE, L.HB_ENEED_BUILD, L.HB_EINVAL)
+    lib.hb_index_free(h)
