@@ -177,6 +177,9 @@ hb_status decode_kv(hb_index* ix, const uint8_t* key, size_t klen, const uint8_t
 }
 
 int64_t slot_of(const hb_index* ix, uint32_t id) {
+    const size_t n = ix->ids.size();
+    if (n && (uint64_t)ix->ids[n - 1] - ix->ids[0] == n - 1)  // strictly ascending and gap-free: the rank is an offset
+        return (id >= ix->ids[0] && id <= ix->ids[n - 1]) ? (int64_t)(id - ix->ids[0]) : -1;
     auto it = std::lower_bound(ix->ids.begin(), ix->ids.end(), id);
     return (it != ix->ids.end() && *it == id) ? (int64_t)(it - ix->ids.begin()) : -1;
 }
