@@ -371,6 +371,30 @@ class Reader:
             raise
         return cls(h, d, index, device)
 
+    @classmethod
+    def build_from_path(cls, path, index, distance, db_name=None, dimensions=0, M=16, M0=32, ef_construction=100, alpha=1.0, seed=42,
+                        device=0, stats=None):
+        """The items `Writer::add_item` left in an LMDB environment on disk (read by the built-in walker), graph built on the
+        device.  `dimensions` is only needed for a database that was never built (no metadata pair yet).  `export_kv(False)`
+        on the result yields the Metadata / Links pairs to put back."""
+        d = _distance_of(distance)
+        lib = L.lib()
+        h = C.c_void_p()
+        _check(lib.hb_index_begin(d.ID, index, C.byref(h)))
+        try:
+            _check(lib.hb_index_push_lmdb(h, os.fsencode(path), db_name.encode() if db_name else None, None))
+            o = L.BuildOpts(M, M0, ef_construction, alpha, seed, 0, dimensions)
+            st = np.zeros(8, np.uint64)
+            _check(lib.hb_index_build_graph(h, C.byref(o), device, _ptr(st)))
+            if stats is not None:
+                stats.update(batches=int(st[0]), launches=int(st[1]), items=int(st[2]), max_level=int(st[3]), dropped=int(st[4]), cut=int(st[5]),
+                             kernels_ms=int(st[6]), build_call_ms=int(st[7]))
+            _check(lib.hb_index_finalize(h, device))
+        except Exception:
+            lib.hb_index_free(h)
+            raise
+        return cls(h, d, index, device)
+
     def export_kv(self, with_items=True):
         """[(key, value)] in LMDB key order, in the encodings Writer::build writes (hb_index_export_kv)."""
         out = []

@@ -364,3 +364,36 @@ def test_corrupted_data_files_never_fault(tmp_path_factory, seed, n_flips, regio
     if st == L.HB_OK:
         assert lib.hb_index_finalize(h, 0) in (L.HB_OK, L.HB_ECUDA, L.HB_EFORMAT, L.HB_EMISSING_METADATA, L.HB_EUNMATCHING_DISTANCE, L.HB_ENEED_BUILD, L.HB_EINVAL)
     lib.hb_index_free(h)
+
+
+def test_build_from_path_reads_the_items_then_needs_a_device(tmp_path):
+    """Reader.build_from_path on an environment that holds what Writer::add_item left (items, Updated stones, no graph):
+    the walker and the decoder do their part on the host; the build itself is device code (no CPU path)."""
+    db, x = make_db("cosine", 300, 40, seed=6, build=True)
+    pairs = [(bytes(k), bytes(v)) for k, v in db.export_kv(0)]
+    never_built = sorted([(k, v) for k, v in pairs if k[2] == 3] + [(bytes([0, 0, 1]) + int(i).to_bytes(4, "big") + b"\0", b"") for i in range(0, 300, 7)])
+    w = LmdbWriter(fill=0.7)
+    w.put_named("vectors", never_built)
+    w.save(str(tmp_path / "env"))
+    import torch
+    if torch.cuda.is_available():
+        st = {}
+        rd = hb.Reader.build_from_path(str(tmp_path / "env"), 0, hb.Cosine, db_name="vectors", dimensions=40, stats=st)
+        assert rd.n_items() == 300 and st["items"] == 300
+        q = make_vectors(20, 40, seed=1)
+        ids, dist, lens = rd.nns(10).ef_search(64).by_vectors_raw(x[:20])
+        assert (ids[:, 0] == np.arange(20)).all()
+    else:
+        with pytest.raises(hb.MissingMetadata):                   # never built and no dimensions given
+            hb.Reader.build_from_path(str(tmp_path / "env"), 0, hb.Cosine, db_name="vectors")
+        with pytest.raises(hb.HannoyError) as e:
+            hb.Reader.build_from_path(str(tmp_path / "env"), 0, hb.Cosine, db_name="vectors", dimensions=40)
+        assert e.value.status == L.HB_ECUDA and "no CUDA device" in str(e.value)
+        with pytest.raises(hb.MissingMetadata):                   # the plain reader refuses it: nothing was ever built, reader.rs:390-393
+            hb.Reader.open_path(str(tmp_path / "env"), 0, hb.Cosine, db_name="vectors")
+        # items added after a build: metadata + graph + Updated stones -> NeedBuild for the reader (reader.rs:407-416)
+        w2 = LmdbWriter()
+        w2.put_unnamed(sorted(set(pairs) | {p for p in never_built if p[0][2] == 1}))
+        w2.save(str(tmp_path / "env2"))
+        with pytest.raises(hb.NeedBuild):
+            hb.Reader.open_path(str(tmp_path / "env2"), 0, hb.Cosine)
