@@ -139,3 +139,57 @@ def test_cuda_on_reference_built_graphs(gi, metric):
                 assert np.array_equal(got[1][i, :m].view(np.uint32), want[1][i, :m].view(np.uint32))
     ids, _, lens = rk.nns(n).ef_search(n).by_vectors_raw(np.zeros((1, md["dimensions"]), np.float32))
     assert lens[0] == n and set(ids[0].tolist()) == set(md["items"])
+
+
+# ---- the rest of the QueryBuilder surface: candidates, linear scan, by_item + candidates, cancellation -------------------------
+@pytest.mark.parametrize("ci", range(N_CASES))
+def test_oracle_reproduces_committed_option_answers(ci):
+    """options_golden.npz (tests/golden/make_options_golden.py): the oracle's filtered / linear / cancelled answers are pinned
+    like the plain ones, so a change to the oracle's visit() or cancel handling cannot go unnoticed."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    from make_options_golden import answers
+    g = load_case(ci)
+    z = np.load(os.path.join(GOLDEN, "options_golden.npz"))
+    got = answers(oracle_db(g), g, ci)
+    keys = [k for k in z.files if k.startswith(f"c{ci}_")]
+    assert len(keys) == len(got) and len(keys) > 20
+    for k in keys:
+        assert np.array_equal(z[k], got[k[len(f"c{ci}_"):]]), k
+    # the fixture exercises what it claims to: a linear scan, a filtered walk, cancelled and completed queries
+    assert (z[f"c{ci}_linear_ctr"][:, 6] & 2).all() and not (z[f"c{ci}_walk_ctr"][:, 6] & 2).any()
+    assert (z[f"c{ci}_cancel1_ctr"][:, 6] & 8).all() and (z[f"c{ci}_cancel1_len"] <= 10).all()
+    assert set(z[f"c{ci}_walk_ids"][z[f"c{ci}_walk_len"] > 0, 0].tolist()) <= set(z[f"c{ci}_cand_big"].tolist())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ci", range(N_CASES))
+def test_cuda_reproduces_committed_option_answers(ci):
+    """The CUDA engine against the same committed answers (ids, distance bits, lengths, traversal counters, LINEAR /
+    CANCELLED flags), independently of the oracle code on the box."""
+    import hannoy_b200 as hb
+    g = load_case(ci)
+    z = np.load(os.path.join(GOLDEN, "options_golden.npz"))
+    p = f"c{ci}_"
+    db = oracle_db(g)  # only used to encode rows / headers the way the Writer stores them
+    rd = hb.Reader.from_arrays(g["metric"], g["dims"], g["ids"], db.rows(), db.headers(), g["layers"], g["eps"], int(g["max_level"]))
+
+    def same(got, key):
+        ids, dist, lens, ctr = got
+        canc = (lens != 0xFFFFFFFF) & ((lens >> 31) == 1)
+        clean = np.where(lens == 0xFFFFFFFF, lens, lens & 0x7FFFFFFF).astype(np.uint32)
+        assert np.array_equal(clean, z[p + key + "_len"]), key
+        for i, n in enumerate(clean):
+            n = 0 if n == 0xFFFFFFFF else int(n)
+            assert np.array_equal(ids[i, :n], z[p + key + "_ids"][i, :n]), (key, i)
+            assert np.array_equal(dist[i, :n].view(np.uint32), z[p + key + "_dbits"][i, :n]), (key, i)
+        want = z[p + key + "_ctr"]
+        assert np.array_equal(ctr[:, :6].astype(np.uint32), want[:, :6]), key
+        assert np.array_equal((ctr[:, 6] & 2) != 0, (want[:, 6] & 2) != 0), key      # LINEAR
+        assert np.array_equal(canc, (want[:, 6] & 8) != 0), key                       # CANCELLED == Searched::did_cancel
+
+    same(rd.nns(10).ef_search(48).candidates(z[p + "cand_big"]).linear_below(0).by_vectors_raw(g["q"], counters=True), "walk")
+    same(rd.nns(10).ef_search(48).candidates(z[p + "cand_small"]).by_vectors_raw(g["q"], counters=True), "linear")
+    same(rd.nns(5).ef_search(32).candidates(z[p + "cand_big"]).linear_below(0).by_items_raw(g["items"], counters=True), "item")
+    for a in (1, 3, 20):
+        same(rd.nns(10).ef_search(48).with_cancellation(a).by_vectors_raw(g["q"], counters=True), f"cancel{a}")
