@@ -17,6 +17,9 @@ CTR_DIST_UPPER, CTR_DIST_L0, CTR_EXP_UPPER, CTR_EXP_L0, CTR_DEG_UPPER, CTR_DEG_L
 FLAG_FALLBACK, FLAG_LINEAR, FLAG_SLOW_PATH, FLAG_CANCELLED = 1, 2, 4, 8
 LEN_CANCELLED, LEN_NONE = 0x80000000, 0xFFFFFFFF
 
+# development entry points (include/hannoy_b200_dev.h): not part of the drop-in boundary
+DEV_EXPORTS = ["hb_tune", "hb_debug_phases", "hb_debug_trace"]
+
 # every symbol include/hannoy_b200.h declares
 EXPORTS = [
     "hb_metric_name", "hb_metric_from_name", "hb_index_begin", "hb_index_push_kv", "hb_index_push_lmdb", "hb_index_open_lmdb",
@@ -24,7 +27,7 @@ EXPORTS = [
     "hb_index_finalize", "hb_index_free", "hb_index_dimensions", "hb_index_n_items", "hb_index_n_entry_points",
     "hb_index_max_level", "hb_index_version", "hb_index_item_ids", "hb_index_contains_item", "hb_index_item_vector",
     "hb_search_by_vector", "hb_search_by_item", "hb_search_by_vector_device", "hb_exact_knn", "hb_merge_topk_device",
-    "hb_launch_count", "hb_last_error", "hb_tune", "hb_debug_phases", "hb_debug_trace",
+    "hb_launch_count", "hb_last_error", "hb_index_replicate", "hb_index_finalize_replicated", "hb_index_n_devices", "hb_index_device",
     "hb_cancel_token_create", "hb_cancel_token_cancel", "hb_cancel_token_reset", "hb_cancel_token_is_cancelled",
     "hb_cancel_token_free", "hb_shard_group_create", "hb_shard_group_connect", "hb_search_sharded_device", "hb_shard_group_free",
 ]
@@ -69,6 +72,8 @@ def lib():
         "hb_lmdb_scan": (i32, [C.c_char_p, C.c_char_p, C.c_char_p, sz, KV_VISIT, vp, C.POINTER(u64)]),
         "hb_index_from_arrays": (i32, [vp, u32, vp, u64, vp, vp, u32, vp, vp, vp, u32, u32]),
         "hb_index_finalize": (i32, [vp, i32]), "hb_index_free": (None, [vp]),
+        "hb_index_replicate": (i32, [vp, vp, i32]), "hb_index_finalize_replicated": (i32, [vp, vp, i32]),
+        "hb_index_n_devices": (i32, [vp]), "hb_index_device": (i32, [vp, i32]),
         "hb_index_dimensions": (u32, [vp]), "hb_index_n_items": (u64, [vp]),
         "hb_index_n_entry_points": (u32, [vp]), "hb_index_max_level": (u32, [vp]),
         "hb_index_version": (i32, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),

@@ -44,9 +44,11 @@ namespace {
     } while (0)
 
 constexpr uint32_t INBOX_K = 32;
+constexpr int LIST_MAX = (int)FIXED_DEG_MAX;  // longest neighbour list (M0 <= 64); a lane handles entries lane and lane + 32
 
 struct GraphDev {
     uint32_t n = 0, M = 0, M0 = 0;
+    uint32_t stride0 = FIXED_DEG;     // layer-0 cells per item: 32, or 64 when 32 < M0 <= 64 (= DevIndex::nbr0_stride)
     uint32_t* nbr[MAX_LEVELS] = {};   // [n x stride(l)] neighbour slots in arrival order, UINT32_MAX padded
     float* dist[MAX_LEVELS] = {};     // [n x stride(l)] distance owner -> neighbour (ScoredLink, hnsw.rs:30)
     uint32_t* deg[MAX_LEVELS] = {};   // [n]
@@ -56,7 +58,7 @@ struct GraphDev {
     uint32_t* touched = nullptr;      // targets with a non-empty inbox
     uint32_t* n_touched = nullptr;
     unsigned long long* n_dropped = nullptr;
-    __host__ __device__ uint32_t stride(uint32_t l) const { return l == 0 ? FIXED_DEG : M; }
+    __host__ __device__ uint32_t stride(uint32_t l) const { return l == 0 ? stride0 : M; }
     __host__ __device__ uint32_t cap(uint32_t l) const { return l == 0 ? M0 : M; }
 };
 
@@ -154,7 +156,7 @@ __device__ void warp_pair_distance_group(const DevIndex& ix, uint32_t a, const u
 
 // robust_prune (hnsw.rs:567-597): candidates in ascending (distance bits, slot) order in keys[0..n_c); selects at most
 // `cap`; a candidate is dropped as soon as one selected point is closer to it (times alpha) than the query is.
-// sel_slot / sel_dist: per-warp shared memory, 32 entries.  Returns the number selected.
+// sel_slot / sel_dist: per-warp shared memory, LIST_MAX entries.  Returns the number selected.
 __device__ int robust_prune_warp(const DevIndex& ix, const unsigned long long* keys, int n_c, int cap, float alpha, uint32_t* sel_slot,
                                  float* sel_dist) {
     int n_sel = 0;
@@ -201,25 +203,32 @@ __device__ void add_link_node(const PruneLinkParams& P, uint32_t p, uint32_t x, 
         if (lane == 0) { st_cg(&nb[deg], x); st_cg(&nd[deg], dist); st_cg(&P.g.deg[lvl][p], deg + 1); }
         return;
     }
-    // full: robust_prune(links) replaces the list, the new link is not part of it.  The <= 32 links are sorted by
-    // (distance bits, slot) through shared memory: unsorted copy, rank by counting, scatter.
+    // full: robust_prune(links) replaces the list, the new link is not part of it.  The <= LIST_MAX links are sorted by
+    // (distance bits, slot) through shared memory: unsorted copy in skeys[LIST_MAX..), rank by counting, scatter to skeys[0..).
     __syncwarp();
-    unsigned long long key = ~0ull;
-    if (lane < (int)deg) key = ((unsigned long long)__float_as_uint(ld_cg(&nd[lane])) << 32) | ld_cg(&nb[lane]);
-    skeys[32 + lane] = key;
-    __syncwarp();
-    int rank = 0;
-    for (int j = 0; j < (int)deg; ++j) {  // a list may hold a link twice (hnsw.rs:521-522 TODO): ties go by position
-        const unsigned long long kj = skeys[32 + j];
-        rank += (kj < key) || (kj == key && j < lane);
+    unsigned long long key[2] = {~0ull, ~0ull};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int e = lane + 32 * k;
+        if (e < (int)deg) key[k] = ((unsigned long long)__float_as_uint(ld_cg(&nd[e])) << 32) | ld_cg(&nb[e]);
+        skeys[LIST_MAX + e] = key[k];
     }
-    if (lane < (int)deg) skeys[rank] = key;
+    __syncwarp();
+    int rank[2] = {0, 0};
+    for (int j = 0; j < (int)deg; ++j) {  // a list may hold a link twice (hnsw.rs:521-522 TODO): ties go by position
+        const unsigned long long kj = skeys[LIST_MAX + j];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) rank[k] += (kj < key[k]) || (kj == key[k] && j < lane + 32 * k);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        if (lane + 32 * k < (int)deg) skeys[rank[k]] = key[k];
     __syncwarp();
     const int n_sel = robust_prune_warp(P.ix, skeys, (int)deg, (int)cap, P.alpha, s_slot, s_dist);
     __syncwarp();
-    if (lane < (int)stride) {
-        st_cg(&nb[lane], lane < n_sel ? s_slot[lane] : 0xffffffffu);
-        st_cg(&nd[lane], lane < n_sel ? s_dist[lane] : 0.0f);
+    for (int e = lane; e < (int)stride; e += 32) {
+        st_cg(&nb[e], e < n_sel ? s_slot[e] : 0xffffffffu);
+        st_cg(&nd[e], e < n_sel ? s_dist[e] : 0.0f);
     }
     if (lane == 0) st_cg(&P.g.deg[lvl][p], (uint32_t)n_sel);
     __syncwarp();
@@ -228,9 +237,9 @@ __device__ void add_link_node(const PruneLinkParams& P, uint32_t p, uint32_t x, 
 constexpr int PL_WARPS = 4;
 
 __global__ void __launch_bounds__(PL_WARPS * 32) prune_link_kernel(const PruneLinkParams P) {
-    __shared__ uint32_t sh_slot[PL_WARPS][2][32];
-    __shared__ float sh_dist[PL_WARPS][2][32];
-    __shared__ unsigned long long sh_keys[PL_WARPS][64];  // [0,32) sorted, [32,64) unsorted
+    __shared__ uint32_t sh_slot[PL_WARPS][2][LIST_MAX];
+    __shared__ float sh_dist[PL_WARPS][2][LIST_MAX];
+    __shared__ unsigned long long sh_keys[PL_WARPS][2 * LIST_MAX];  // [0, LIST_MAX) sorted, [LIST_MAX, ..) unsorted
     const int wib = threadIdx.x >> 5, lane = lane_id();
     for (uint32_t i = blockIdx.x * PL_WARPS + wib; i < P.n_items; i += gridDim.x * PL_WARPS) {
     const uint32_t q = P.items[i];
@@ -241,17 +250,18 @@ __global__ void __launch_bounds__(PL_WARPS * 32) prune_link_kernel(const PruneLi
     const int n_c = (int)P.cand_len[i];
     const int n_sel = robust_prune_warp(P.ix, P.cand + (size_t)i * P.efc, n_c, (int)P.own_cap, P.alpha, sel_slot, sel_dist);
     __syncwarp();
-    P.sel_out[(size_t)i * 32 + lane] = lane < n_sel ? sel_slot[lane] : 0xffffffffu;   // eps.push(n), hnsw.rs:323
+    // eps.push(n), hnsw.rs:323 — read by the walk one layer down, where at most M <= 32 were selected (on layer 0 nobody reads it)
+    P.sel_out[(size_t)i * 32 + lane] = lane < n_sel ? sel_slot[lane] : 0xffffffffu;
     // add_link(query, (dist, n)) for every selected n — hnsw.rs:320.  q is not linked yet: its list is this warp's alone.
     for (int j = 0; j < n_sel; ++j) add_link_node(P, q, sel_slot[j], sel_dist[j], sh_keys[wib], sh_slot[wib][1], sh_dist[wib][1]);
     // add_link(n, (dist, query)) — hnsw.rs:321 — is posted to n's inbox
-    if (lane < n_sel) {
-        const uint32_t t = sel_slot[lane];
+    for (int e = lane; e < n_sel; e += 32) {
+        const uint32_t t = sel_slot[e];
         if (t != q) {
-            if (t >= P.ix.n) build_fail(4, q, t, (unsigned)lane, (unsigned)n_sel);
+            if (t >= P.ix.n) build_fail(4, q, t, (unsigned)e, (unsigned)n_sel);
             else {
                 const uint32_t pos = atomicAdd(&P.g.inbox_cnt[t], 1u);
-                if (pos < INBOX_K) P.g.inbox[(size_t)t * INBOX_K + pos] = ((unsigned long long)__float_as_uint(sel_dist[lane]) << 32) | q;
+                if (pos < INBOX_K) P.g.inbox[(size_t)t * INBOX_K + pos] = ((unsigned long long)__float_as_uint(sel_dist[e]) << 32) | q;
                 else atomicAdd(P.g.n_dropped, 1ull);
                 if (pos == 0) P.g.touched[atomicAdd(P.g.n_touched, 1u)] = t;
             }
@@ -264,10 +274,11 @@ __global__ void __launch_bounds__(PL_WARPS * 32) prune_link_kernel(const PruneLi
 // The reverse half of the batch's links: one warp per target that received any, sources applied in ascending
 // (distance bits, slot) order.
 __global__ void __launch_bounds__(PL_WARPS * 32) apply_reverse_kernel(const PruneLinkParams P) {
-    __shared__ uint32_t sh_slot[PL_WARPS][32];
-    __shared__ float sh_dist[PL_WARPS][32];
-    __shared__ unsigned long long sh_keys[PL_WARPS][64];
+    __shared__ uint32_t sh_slot[PL_WARPS][LIST_MAX];
+    __shared__ float sh_dist[PL_WARPS][LIST_MAX];
+    __shared__ unsigned long long sh_keys[PL_WARPS][2 * LIST_MAX];
     __shared__ unsigned long long sh_in[PL_WARPS][INBOX_K];
+    __shared__ unsigned long long sh_raw[PL_WARPS][INBOX_K];
     const int wib = threadIdx.x >> 5, lane = lane_id();
     const uint32_t n_t = *P.g.n_touched;
     for (uint32_t i = blockIdx.x * PL_WARPS + wib; i < n_t; i += gridDim.x * PL_WARPS) {
@@ -275,11 +286,11 @@ __global__ void __launch_bounds__(PL_WARPS * 32) apply_reverse_kernel(const Prun
         const uint32_t cnt = min(P.g.inbox_cnt[t], INBOX_K);
         unsigned long long rec = ~0ull;
         if (lane < (int)cnt) rec = P.g.inbox[(size_t)t * INBOX_K + lane];
-        sh_keys[wib][32 + lane] = rec;
+        sh_raw[wib][lane] = rec;
         __syncwarp();
         int rank = 0;
         for (uint32_t j = 0; j < cnt; ++j) {
-            const unsigned long long rj = sh_keys[wib][32 + j];
+            const unsigned long long rj = sh_raw[wib][j];
             rank += (rj < rec) || (rj == rec && (int)j < lane);
         }
         if (lane < (int)cnt) sh_in[wib][rank] = rec;
@@ -336,8 +347,9 @@ hb_status build_graph_on_device(hb_index* ix, uint32_t M, uint32_t M0, uint32_t 
     const auto t_start = std::chrono::steady_clock::now();
     auto ms_since = [](std::chrono::steady_clock::time_point t0) { return (uint64_t)std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count(); };
     const size_t n = ix->ids.size();
-    if (M < 2 || M > 32 || M0 < 2 || M0 > FIXED_DEG || efc < 1 || efc > 4096) { set_error("hb_index_build_graph: need 2 <= M <= 32, 2 <= M0 <= 32, 1 <= ef_construction <= 4096"); return HB_EINVAL; }
-    if (n >= 0xfffffff0ull / 32) { set_error("too many items"); return HB_EINVAL; }
+    if (M < 2 || M > 32 || M0 < 2 || M0 > FIXED_DEG_MAX || efc < 1 || efc > 4096) { set_error("hb_index_build_graph: need 2 <= M <= 32, 2 <= M0 <= 64, 1 <= ef_construction <= 4096"); return HB_EINVAL; }
+    const uint32_t stride0 = M0 <= FIXED_DEG ? FIXED_DEG : FIXED_DEG_MAX;
+    if (n >= 0xfffffff0ull / stride0) { set_error("too many items"); return HB_EINVAL; }
     ix->layers.clear();
     ix->eps.clear();
     ix->max_level = 0;
@@ -390,7 +402,7 @@ hb_status build_graph_on_device(hb_index* ix, uint32_t M, uint32_t M0, uint32_t 
     d.n_layers = L + 1;
     d.max_level = L;
     GraphDev g;
-    g.n = (uint32_t)n; g.M = M; g.M0 = M0;
+    g.n = (uint32_t)n; g.M = M; g.M0 = M0; g.stride0 = stride0;
     for (uint32_t l = 0; l <= L; ++l) {
         const size_t cells = n * (size_t)g.stride(l);
         if ((st = fr.alloc(&g.nbr[l], cells)) != HB_OK || (st = fr.alloc(&g.dist[l], cells)) != HB_OK || (st = fr.alloc(&g.deg[l], n)) != HB_OK)
@@ -411,6 +423,7 @@ hb_status build_graph_on_device(hb_index* ix, uint32_t M, uint32_t M0, uint32_t 
     fill_stride_offsets_kernel<<<(unsigned)((n + 1 + 255) / 256), 256>>>(d_off, n + 1, M);
     g_launches += 1;
     d.nbr0x = g.nbr[0];
+    d.nbr0_stride = stride0;
     for (uint32_t l = 1; l <= L; ++l) { d.off[l] = d_off; d.nbr[l] = g.nbr[l]; }
     uint32_t* d_eps = nullptr;
     if ((st = fr.alloc(&d_eps, eps.size())) != HB_OK) return st;

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cctype>
 #include <cstring>
+#include <thread>
 
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -180,20 +181,9 @@ hb_status hb_index_build_graph(hb_index* ix, const hb_build_opts* opts, int devi
         hb_build_opts o = {16, 32, 100, 1.0f, 42, 0, 0};
         if (opts) o = *opts;
         if (ix->ids.empty() && (ix->have_metadata || !ix->kv_items.empty())) {   // items came through push_kv / push_lmdb
-            if (!ix->have_metadata) {
-                // a database that was never built has no metadata yet (the Writer writes it in build(), writer.rs:521-603):
-                // every Item node is an item, the dimensions come from the caller
-                if (!o.dimensions) { set_error("hb_index_build_graph: the database has no metadata, pass hb_build_opts.dimensions"); return HB_EMISSING_METADATA; }
-                ix->meta_distance = hb_metric_name(ix->metric);
-                ix->meta_dims = o.dimensions;
-                ix->meta_items.clear();
-                for (auto& kv : ix->kv_items) ix->meta_items.push_back(kv.first);  // std::map: ascending
-                ix->meta_eps.clear();
-                ix->meta_max_level = 0;
-                ix->have_metadata = true;
-            }
-            ix->need_build = false;                                                // building is what this call is for
-            hb_status st = build_host_snapshot_from_kv(ix);
+            // a database that was never built has no metadata yet (the Writer writes it in build(), writer.rs:521-603): the
+            // dimensions then come from the caller.  Either way the item set is the Item nodes present, not the stored bitmap.
+            hb_status st = build_host_items_for_build(ix, o.dimensions);
             if (st != HB_OK) return st;
         }
         if (ix->version[0] == 0 && ix->version[1] == 0 && ix->version[2] == 0) { ix->version[1] = 1; ix->version[2] = 3; }
@@ -281,16 +271,27 @@ hb_status hb_index_from_arrays(hb_index* ix, uint32_t dims, const uint32_t* ids,
         if (hdr) ix->host_hdr.assign(hdr, hdr + n);
         else ix->host_hdr.assign(n, 0.0f);
         ix->layers.assign(n_layers, HostLayer());
+        if (n_layers && (!offsets || !nbrs)) { set_error("hb_index_from_arrays: null offsets/nbrs"); return HB_EINVAL; }
         for (uint32_t l = 0; l < n_layers; ++l) {
+            // the arrays are trusted by the kernels: same checks as hb_index_load (snapshot.cpp)
             HostLayer& hl = ix->layers[l];
+            if (!offsets[l]) { set_error("layer %u: null offsets", l); return HB_EINVAL; }
             hl.off.assign(offsets[l], offsets[l] + n + 1);
+            if (hl.off[0] != 0) { set_error("layer %u: offsets must start at 0", l); return HB_EFORMAT; }
+            for (uint64_t i = 0; i < n; ++i)
+                if (hl.off[i + 1] < hl.off[i]) { set_error("layer %u: offsets are not monotone at item %llu", l, (unsigned long long)i); return HB_EFORMAT; }
             uint64_t nnz = n ? hl.off[n] : 0;
+            if (nnz >= 0xffffffffull) { set_error("layer %u has too many edges for 32-bit offsets", l); return HB_EFORMAT; }
+            if (nnz && !nbrs[l]) { set_error("layer %u: null neighbour array", l); return HB_EINVAL; }
             hl.nbr.resize(nnz);
             for (uint64_t e = 0; e < nnz; ++e) {
                 int64_t s = slot_of(ix, nbrs[l][e]);
                 if (s < 0) { set_error("layer %u: neighbour id %u is not an item", l, nbrs[l][e]); return HB_EFORMAT; }
                 hl.nbr[e] = (uint32_t)s;
             }
+            for (uint64_t i = 0; i < n; ++i)      // roaring iteration order (reader.rs:342): strictly ascending in every list
+                for (uint64_t e = hl.off[i] + 1; e < hl.off[i + 1]; ++e)
+                    if (hl.nbr[e] <= hl.nbr[e - 1]) { set_error("layer %u: neighbours of item %u are not strictly ascending", l, ids[i]); return HB_EFORMAT; }
         }
         ix->eps.clear();
         for (uint32_t i = 0; i < n_ep; ++i) {
@@ -363,6 +364,7 @@ static hb_status upload(hb_index* ix, const T* host, size_t count, const T** out
     size_t bytes = std::max<size_t>(count * sizeof(T), 16);
     CUDA_TRY(cudaMalloc(&d, bytes));
     ix->dev_allocs.push_back(d);
+    ix->dev_alloc_bytes.push_back(bytes);
     if (count) CUDA_TRY(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
     *out = (const T*)d;
     return HB_OK;
@@ -393,6 +395,7 @@ hb_status hb_index_finalize(hb_index* ix, int device) {
     DevIndex& d = ix->dev;
     size_t n = ix->ids.size();
     if ((st = setup_dev_rows(ix, d, ix->dev_allocs)) != HB_OK) return st;
+    while (ix->dev_alloc_bytes.size() < ix->dev_allocs.size()) ix->dev_alloc_bytes.push_back(std::max<size_t>(n * (size_t)d.row_stride, 16));
     d.max_level = ix->max_level;
     d.n_layers = (uint32_t)ix->layers.size();
     if (d.n_layers > (uint32_t)MAX_LEVELS) { set_error("too many layers"); return HB_EINVAL; }
@@ -410,11 +413,14 @@ hb_status hb_index_finalize(hb_index* ix, int device) {
         const HostLayer& l0 = ix->layers[0];
         uint64_t max_deg = 0;
         for (size_t i = 0; i < n; ++i) max_deg = std::max<uint64_t>(max_deg, l0.off[i + 1] - l0.off[i]);
-        if (max_deg <= FIXED_DEG) {
-            std::vector<uint32_t> fx(n * (size_t)FIXED_DEG, 0xffffffffu);
+        if (max_deg <= FIXED_DEG_MAX) {
+            // one 128-byte line per item, two for graphs built with 32 < M0 <= 64 (longer lists stay on the CSR path)
+            const size_t stride = max_deg <= FIXED_DEG ? FIXED_DEG : FIXED_DEG_MAX;
+            std::vector<uint32_t> fx(n * stride, 0xffffffffu);
             for (size_t i = 0; i < n; ++i)
-                std::copy(l0.nbr.begin() + l0.off[i], l0.nbr.begin() + l0.off[i + 1], fx.begin() + i * FIXED_DEG);
+                std::copy(l0.nbr.begin() + l0.off[i], l0.nbr.begin() + l0.off[i + 1], fx.begin() + i * stride);
             if ((st = upload(ix, fx.data(), fx.size(), &d.nbr0x)) != HB_OK) return st;
+            d.nbr0_stride = (uint32_t)stride;
         }
     }
     if ((st = upload(ix, ix->eps.data(), ix->eps.size(), &d.eps)) != HB_OK) return st;
@@ -422,6 +428,82 @@ hb_status hb_index_finalize(hb_index* ix, int device) {
     ix->finalized = true;
     return HB_OK;
 }
+
+// ---- replicas on further devices (SURVEY §8b `hb_index_finalize(ix, devices, n_dev, ..)`, §8e) ----------------------------
+// Every device buffer of the finalized index is copied device-to-device (NVLink when the GPUs are peers), and the pointers
+// of the DevIndex are re-based onto the copies.
+static hb_status replicate_one(const hb_index* ix, int device, hb_index** out) {
+    hb_index* r = new (std::nothrow) hb_index();
+    if (!r) return HB_ENOMEM;
+    r->metric = ix->metric; r->index = ix->index; r->dims = ix->dims; r->finalized = true; r->device = device; r->primary = ix;
+    std::vector<std::pair<const uint8_t*, size_t>> ranges;
+    auto fail = [&](hb_status st) { hb_index_free(r); return st; };
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(cudaGetLastError())); return fail(HB_ECUDA); }
+    for (size_t a = 0; a < ix->dev_allocs.size(); ++a) {
+        void* base = ix->dev_allocs[a];
+        const size_t bytes = ix->dev_alloc_bytes[a];
+        void* cp = nullptr;
+        if (cudaMalloc(&cp, bytes) != cudaSuccess) { set_error("device %d: allocation of %zu bytes failed", device, bytes); cudaGetLastError(); return fail(HB_ENOMEM); }
+        r->dev_allocs.push_back(cp);
+        if (cudaMemcpyPeer(cp, device, base, ix->device, bytes) != cudaSuccess) { set_error("cudaMemcpyPeer %d -> %d failed: %s", ix->device, device, cudaGetErrorString(cudaGetLastError())); return fail(HB_ECUDA); }
+        ranges.push_back({(const uint8_t*)base, bytes});
+    }
+    auto rebase = [&](const void* p) -> const void* {
+        if (!p) return nullptr;
+        for (size_t i = 0; i < ranges.size(); ++i)
+            if ((const uint8_t*)p >= ranges[i].first && (const uint8_t*)p < ranges[i].first + ranges[i].second)
+                return (const uint8_t*)r->dev_allocs[i] + ((const uint8_t*)p - ranges[i].first);
+        return nullptr;
+    };
+    r->dev = ix->dev;
+    DevIndex& d = r->dev;
+    d.rows = (const uint8_t*)rebase(ix->dev.rows); d.hdr = (const float*)rebase(ix->dev.hdr); d.ids = (const uint32_t*)rebase(ix->dev.ids);
+    d.eps = (const uint32_t*)rebase(ix->dev.eps); d.nbr0x = (const uint32_t*)rebase(ix->dev.nbr0x);
+    for (uint32_t l = 0; l < d.n_layers; ++l) { d.off[l] = (const uint32_t*)rebase(ix->dev.off[l]); d.nbr[l] = (const uint32_t*)rebase(ix->dev.nbr[l]); }
+    if (cudaDeviceSynchronize() != cudaSuccess) { set_error("replication to device %d failed: %s", device, cudaGetErrorString(cudaGetLastError())); return fail(HB_ECUDA); }
+    *out = r;
+    return HB_OK;
+}
+
+extern "C" {
+
+hb_status hb_index_replicate(hb_index* ix, const int* devices, int n_dev) {
+    if (!ix || (n_dev > 0 && !devices) || n_dev < 0) { set_error("hb_index_replicate: bad arguments"); return HB_EINVAL; }
+    if (!ix->finalized || ix->primary) { set_error("hb_index_replicate: finalize the index first"); return HB_ESTATE; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device available (libhannoy_b200 has no CPU path)"); return HB_ECUDA; }
+    for (int i = 0; i < n_dev; ++i) {
+        // (a device may be named more than once: it then holds several copies, each with its own stream and workspaces)
+        if (devices[i] < 0 || devices[i] >= ndev) { set_error("bad device %d", devices[i]); return HB_EINVAL; }
+    }
+    try {
+        for (int i = 0; i < n_dev; ++i) {
+            hb_index* r = nullptr;
+            hb_status st = replicate_one(ix, devices[i], &r);
+            if (st != HB_OK) return st;
+            ix->replicas.push_back(r);
+        }
+    } catch (const std::bad_alloc&) {
+        return HB_ENOMEM;
+    }
+    cudaSetDevice(ix->device);
+    return HB_OK;
+}
+
+hb_status hb_index_finalize_replicated(hb_index* ix, const int* devices, int n_dev) {
+    if (!ix || !devices || n_dev < 1) { set_error("hb_index_finalize_replicated: bad arguments"); return HB_EINVAL; }
+    hb_status st = hb_index_finalize(ix, devices[0]);
+    if (st != HB_OK) return st;
+    return hb_index_replicate(ix, devices + 1, n_dev - 1);
+}
+
+int hb_index_n_devices(const hb_index* ix) { return ix ? 1 + (int)ix->replicas.size() : 0; }
+int hb_index_device(const hb_index* ix, int i) {
+    if (!ix || i < 0 || i > (int)ix->replicas.size()) return -1;
+    return i == 0 ? ix->device : ix->replicas[i - 1]->device;
+}
+
+}  // extern "C"
 
 static void free_workspace(Workspace* w) {
     if (!w) return;
@@ -434,6 +516,8 @@ static void free_workspace(Workspace* w) {
 
 void hb_index_free(hb_index* ix) {
     if (!ix) return;
+    for (hb_index* r : ix->replicas) hb_index_free(r);
+    ix->replicas.clear();
     if (ix->device >= 0) cudaSetDevice(ix->device);
     for (Workspace* w : ix->ws_all) free_workspace(w);
     for (void* p : ix->dev_allocs) cudaFree(p);
@@ -487,7 +571,7 @@ static hb_status make_workspace(hb_index* ix, Workspace** out) {
     int bps = 64 / SEARCH_WARPS_PER_BLOCK;  // one visited bitset per warp the hardware can keep resident
     w->n_sm = prop.multiProcessorCount;
     w->n_slots = prop.multiProcessorCount * bps * SEARCH_WARPS_PER_BLOCK;
-    size_t n = ix->ids.size();
+    size_t n = ix->host()->ids.size();
     w->vis_words = (uint32_t)(((n + 31) / 32 + 31) / 32 * 32);
     if (w->vis_words == 0) w->vis_words = 32;
     w->touched_cap = (uint32_t)std::max(1024, tunable("touched_cap", 16384));
@@ -497,7 +581,7 @@ static hb_status make_workspace(hb_index* ix, Workspace** out) {
     CUDA_TRY(cudaMalloc(&w->work_counter, 16));
     CUDA_TRY(cudaMalloc(&w->n_overflow, 16));
     CUDA_TRY(cudaMemset(w->n_overflow, 0, 16));
-    w->gheap_entries_per_slot = 2 * (uint64_t)(n + ix->eps.size() + 64);
+    w->gheap_entries_per_slot = 2 * (uint64_t)(n + ix->host()->eps.size() + 64);
     uint64_t per_slot = w->gheap_entries_per_slot * 8;
     int slow = (int)std::min<uint64_t>(64, std::max<uint64_t>(4, (512ull << 20) / per_slot));
     slow = slow / SEARCH_WARPS_PER_BLOCK * SEARCH_WARPS_PER_BLOCK;
@@ -570,6 +654,7 @@ static hb_status run_search(const hb_index* ix, Workspace* w, SearchParams base,
     base.n_work = (uint32_t)nq;
     base.q_smem_bytes = (d.row_stride + 15) & ~15u;
     base.defer = tunable("defer", 1);
+    base.team = tunable("team", 1);
     const uint32_t ef0 = std::max(base.ef_raw, base.count);
     if (d.kind == KIND_F32_WARP && d.row_stride >= (uint32_t)tunable("ring_min_row", 0)) {
         // rows in flight per warp: as many as fit the ring budget, in whole reduction groups (512-byte rows: the
@@ -634,8 +719,10 @@ struct hb_cancel_token {
     std::atomic<int> cancelled{0};
 };
 
-static hb_status search_host(const hb_index* ix, const float* q, const uint32_t* items, uint64_t nq, uint32_t count, uint32_t ef,
-                             const hb_query_opts* opts, uint32_t* out_ids, float* out_dist, uint32_t* out_len, uint64_t* out_ctr) {
+// One device: `dx` holds the device state (the primary itself or one of its replicas), its host() the snapshot.
+static hb_status search_host_one(const hb_index* dx, const float* q, const uint32_t* items, uint64_t nq, uint32_t count, uint32_t ef,
+                                 const hb_query_opts* opts, uint32_t* out_ids, float* out_dist, uint32_t* out_len, uint64_t* out_ctr) {
+    const hb_index* ix = dx->host();
     const bool by_item = items != nullptr;
     const size_t n = ix->ids.size();
     if (nq == 0) return HB_OK;
@@ -659,7 +746,7 @@ static hb_status search_host(const hb_index* ix, const float* q, const uint32_t*
     bool linear = has_cand && should_linear_scan(n, ci.slots.size(), opts);
     const hb_cancel_token* tok = opts ? opts->cancel : nullptr;
     const uint64_t cancel_after = opts ? opts->cancel_after_polls : 0;
-    if (tok && tok->device != ix->device) { set_error("the cancel token lives on device %d, the index on %d", tok->device, ix->device); return HB_EINVAL; }
+    if (tok && tok->device != dx->device) { set_error("the cancel token lives on device %d, the index on %d", tok->device, dx->device); return HB_EINVAL; }
     int linear_cancelled = 0;
     std::vector<uint32_t> scan_slots;  // linear scan under a poll budget: cancel_fn is called once per candidate id,
     if (linear && cancel_after) {      // present or not (reader.rs:683-687) -> the scan stops before candidate number cancel_after
@@ -672,12 +759,12 @@ static hb_status search_host(const hb_index* ix, const float* q, const uint32_t*
     const std::vector<uint32_t>& lin_slots = (linear && cancel_after) ? scan_slots : ci.slots;
     if (count == 0 && !by_item) { none(0); return HB_OK; }
 
-    CUDA_TRY(cudaSetDevice(ix->device));
+    CUDA_TRY(cudaSetDevice(dx->device));
     Workspace* w = nullptr;
-    hb_status st = acquire_ws(ix, &w);
+    hb_status st = acquire_ws(dx, &w);
     if (st != HB_OK) return st;
     cudaStream_t stream = (cudaStream_t)w->stream;
-    auto fail = [&](hb_status s) { release_ws(ix, w); return s; };
+    auto fail = [&](hb_status s) { release_ws(dx, w); return s; };
 
     size_t q_bytes = by_item ? nq * 4 : nq * (size_t)ix->dims * 4;
     if ((st = grow(&w->d_q, &w->d_q_bytes, q_bytes)) != HB_OK) return fail(st);
@@ -716,7 +803,7 @@ static hb_status search_host(const hb_index* ix, const float* q, const uint32_t*
     uint8_t* ob = (uint8_t*)w->d_out;
     p.out_ids = (uint32_t*)ob; p.out_dist = (float*)(ob + off_dist); p.out_len = (uint32_t*)(ob + off_len);
     p.out_ctr = out_ctr ? (uint64_t*)(ob + off_ctr) : nullptr;
-    if ((st = run_search(ix, w, p, stream)) != HB_OK) return fail(st);
+    if ((st = run_search(dx, w, p, stream)) != HB_OK) return fail(st);
     if (ids_b) {
         cudaMemcpyAsync(out_ids, p.out_ids, ids_b, cudaMemcpyDeviceToHost, stream);
         cudaMemcpyAsync(out_dist, p.out_dist, ids_b, cudaMemcpyDeviceToHost, stream);
@@ -726,7 +813,47 @@ static hb_status search_host(const hb_index* ix, const float* q, const uint32_t*
     cudaError_t e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) { set_error("search failed: %s", cudaGetErrorString(e)); return fail(HB_ECUDA); }
     w->async_used = false;  // drained
-    release_ws(ix, w);
+    release_ws(dx, w);
+    return HB_OK;
+}
+
+// hb_search_by_vector / hb_search_by_item.  A replicated index (hb_index_replicate; SURVEY §8e "replicas only, partition
+// the query batch") splits the batch into contiguous slices, one per device, each searched by its own host thread on its
+// own stream; there is no collective, the slices land in the caller's buffers directly.
+static hb_status search_host(const hb_index* ix, const float* q, const uint32_t* items, uint64_t nq, uint32_t count, uint32_t ef,
+                             const hb_query_opts* opts, uint32_t* out_ids, float* out_dist, uint32_t* out_len, uint64_t* out_ctr) {
+    const size_t G = 1 + ix->replicas.size();
+    if (G == 1 || nq < 2) return search_host_one(ix, q, items, nq, count, ef, opts, out_ids, out_dist, out_len, out_ctr);
+    if (opts && opts->cancel) {  // a cancel token lives on one device: the whole batch runs there
+        const hb_index* on = ix->device == opts->cancel->device ? ix : nullptr;
+        for (const hb_index* r : ix->replicas) if (!on && r->device == opts->cancel->device) on = r;
+        if (!on) { set_error("the cancel token lives on device %d, which holds no replica of the index", opts->cancel->device); return HB_EINVAL; }
+        return search_host_one(on, q, items, nq, count, ef, opts, out_ids, out_dist, out_len, out_ctr);
+    }
+    std::vector<hb_status> st(G, HB_OK);
+    std::vector<std::string> msg(G);
+    const size_t dims = ix->dims;
+    auto run = [&](size_t g) {
+        const uint64_t base = nq / G, rem = nq % G;
+        const uint64_t lo = g * base + std::min<uint64_t>(g, rem), cnt = base + (g < rem ? 1 : 0);
+        if (cnt == 0) return;
+        const hb_index* dx = g == 0 ? ix : ix->replicas[g - 1];
+        try {
+            st[g] = search_host_one(dx, q ? q + lo * dims : nullptr, items ? items + lo : nullptr, cnt, count, ef, opts,
+                                    out_ids ? out_ids + lo * count : nullptr, out_dist ? out_dist + lo * count : nullptr, out_len + lo,
+                                    out_ctr ? out_ctr + lo * HB_N_CTR : nullptr);
+        } catch (const std::bad_alloc&) {
+            st[g] = HB_ENOMEM;
+        }
+        if (st[g] != HB_OK) msg[g] = last_error();
+    };
+    if (!out_len) { set_error("null output buffer"); return HB_EINVAL; }
+    std::vector<std::thread> th;
+    for (size_t g = 1; g < G; ++g) th.emplace_back(run, g);
+    run(0);
+    for (auto& t : th) t.join();
+    for (size_t g = 0; g < G; ++g)
+        if (st[g] != HB_OK) { set_error("device %d: %s", (g == 0 ? ix : ix->replicas[g - 1])->device, msg[g].c_str()); return st[g]; }
     return HB_OK;
 }
 

@@ -49,11 +49,14 @@ struct DevIndex {
     const uint32_t* nbr[MAX_LEVELS] = {};  // per layer: neighbour SLOTS, ascending in each list
     const uint32_t* eps = nullptr;         // entry point slots, metadata order
     uint32_t n_ep = 0;
-    // layer 0 again, fixed stride: FIXED_DEG slots per item, ascending, padded with UINT32_MAX — one aligned
-    // 128-byte line per expansion instead of two dependent CSR reads.  nullptr if some layer-0 list is longer.
+    // layer 0 again, fixed stride: nbr0_stride (32 or 64) slots per item, ascending, padded with UINT32_MAX — one
+    // aligned 128-byte line per expansion (two for graphs with 32 < M0 <= 64, the second only read when the first is
+    // full) instead of two dependent CSR reads.  nullptr if some layer-0 list is longer than FIXED_DEG_MAX.
     const uint32_t* nbr0x = nullptr;
+    uint32_t nbr0_stride = 32;
 };
-constexpr uint32_t FIXED_DEG = 32;
+constexpr uint32_t FIXED_DEG = 32;       // one adjacency line
+constexpr uint32_t FIXED_DEG_MAX = 64;   // widest fixed-stride layer-0 list (M0 = 48 / 64 of the reference's bindings, python.rs:280)
 constexpr int HB_MAX_SHARDS = 16;
 
 // One search call.
@@ -101,6 +104,8 @@ struct SearchParams {
     int no_trim = 0;                   // graph builder, metrics with negative distances: shared-memory heaps without dead-entry trimming,
                                        // no deferred pops (the literal reference loop); a negative distance does not end the walk
     int defer = 1;                     // layer 0, pass 0: overlap a chunk's heap update with the next pop's adjacency / visited traffic
+    int team = 1;                      // f32 ring kernel: warps of a CTA that ran out of queries gather rows for the ones still walking
+    uint32_t n_static = 0;             // queries handed out by position (warp w of CTA b starts with query w * gridDim + b), the rest by counter
 };
 // One batch of the device graph builder's candidate search (search.cu build_search_kernel): `walk_layer` of
 // src/hnsw.rs:460-519 for every item of the batch on layer `level` with ef = efc, optionally preceded by the greedy
@@ -183,8 +188,15 @@ struct hb_index {
     uint32_t max_level = 0;
     std::vector<uint32_t> node_level;  // per slot, set by the device graph builder: the item has a Links node on layers 0..node_level
     // --- device ---
+    // A replica (hb_index_replicate) is an hb_index that holds device state only: `primary` owns the host snapshot
+    // (ids, dims, eps, ...) that the host side of a search reads; `replicas` of the primary are searched by
+    // hb_search_by_vector / hb_search_by_item on contiguous slices of the batch, one host thread + stream per device.
+    const hb_index* primary = nullptr;
+    std::vector<hb_index*> replicas;
+    const hb_index* host() const { return primary ? primary : this; }
     hb::DevIndex dev;
     std::vector<void*> dev_allocs;
+    std::vector<size_t> dev_alloc_bytes;  // parallel to dev_allocs (replication copies buffer by buffer)
     std::mutex ws_mu;
     std::vector<hb::Workspace*> ws_free;
     std::vector<hb::Workspace*> ws_all;
@@ -195,6 +207,7 @@ void set_error(const char* fmt, ...);
 // snapshot.cpp
 hb_status decode_kv(hb_index* ix, const uint8_t* key, size_t klen, const uint8_t* val, size_t vlen);
 hb_status build_host_snapshot_from_kv(hb_index* ix);
+hb_status build_host_items_for_build(hb_index* ix, uint32_t dims_opt);
 bool roaring_decode(const uint8_t* p, size_t len, std::vector<uint32_t>& out);
 int64_t slot_of(const hb_index* ix, uint32_t id);
 hb_status snapshot_save(const hb_index* ix, const char* path);

@@ -99,6 +99,9 @@ hb_status pick_meta(const File& f, Meta* out) {
     if (ps < 512 || ps > 65536 || (ps & (ps - 1))) { set_error("lmdb: implausible page size %u", ps); return HB_EFORMAT; }
     bool ok1 = read_meta(f, ps, &m1) && m1.psize == ps;
     *out = (ok1 && m1.txnid > m0.txnid) ? m1 : m0;
+    const uint64_t n_file_pages = f.size / ps;
+    if (n_file_pages < 2) { set_error("lmdb: data file shorter than its two meta pages"); return HB_EFORMAT; }
+    if (out->last_pg > n_file_pages - 1) out->last_pg = n_file_pages - 1;  // untrusted: never beyond the mapping
     return HB_OK;
 }
 
@@ -113,7 +116,9 @@ struct Walker {
     hb_status st = HB_OK;
 
     const uint8_t* page(uint64_t pgno, uint64_t n_pages = 1) {
-        if (pgno > meta.last_pg || pgno + n_pages - 1 > meta.last_pg || (pgno + n_pages) * (uint64_t)meta.psize > f.size) {
+        // compared in page units: `(pgno + n_pages) * psize` can wrap for page numbers taken from a damaged file
+        const uint64_t n_file_pages = f.size / meta.psize;
+        if (n_pages == 0 || pgno > meta.last_pg || pgno >= n_file_pages || n_pages > n_file_pages - pgno || n_pages - 1 > meta.last_pg - pgno) {
             set_error("lmdb: page %llu (+%llu) outside the data file", (unsigned long long)pgno, (unsigned long long)n_pages);
             st = HB_EFORMAT;
             return nullptr;

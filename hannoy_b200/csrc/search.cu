@@ -14,7 +14,12 @@
 //   * layer-0 adjacency is read from a fixed-stride copy (one aligned 128-byte line per expansion) and the
 //     line of the most likely next candidate is requested while the current rows are in flight;
 //   * queries whose heaps outgrow shared memory are re-run by a second pass of the same code with
-//     heaps in global memory (never on the CPU).
+//     heaps in global memory (never on the CPU);
+//   * a warp that finds no query left does not retire: it becomes a helper of the warps of its CTA that are still
+//     walking and gathers a share of the rows of each of their expansions through its own ring (TeamShared below) —
+//     the tail of a big batch, a batch smaller than the resident warps (one 10k batch split over 8 GPUs) and a
+//     single query all get up to 4 rings per query instead of one.
+#include <algorithm>
 #include <cfloat>
 #include <cstdio>
 #include <cstdlib>
@@ -80,6 +85,8 @@ struct Ctx {
     uint32_t polls;                       // calls of cancel_fn made by this query so far
     bool tr;                              // this warp writes the event trace (HB_TRACE builds)
     RowRing& ring;                        // per-warp, lives across queries (barrier phases persist)
+    struct TeamShared* ts = nullptr;      // CTA-shared helper state (f32 ring kernel), or nullptr
+    uint32_t* team = nullptr;             // per-warp: bits 0-3 helpers attached to this warp, bits 4-7 their done-barrier parities
 #ifdef HB_PHASES
     long long ph[PH_N];
 #endif
@@ -268,6 +275,145 @@ __device__ __forceinline__ float rows_finish(Ctx& c, const RowsInFlight& rf, uin
     return mine;
 }
 
+// ---- team: idle warps of a CTA gather rows for the ones still walking -----------------------------------------------------
+// Work is handed out per warp; a warp that finds the counter exhausted marks itself FREE and waits on its job barrier.  A
+// warp that is still walking (a "leader") claims FREE warps of its CTA (atomicCAS on owner[h]) and from then on splits
+// the live rows of every chunk: it keeps the first share, posts the slots of the others into the helpers' mailboxes
+// (mbarrier arrive = release), gathers its own share, then waits for the helpers' done barriers and picks their
+// distances up.  A helper computes the whole D::distance of its rows with the same warp-wide routine (rows_begin /
+// rows_finish through its own ring) against the leader's staged query, so every value is bit-identical to what the
+// leader would have computed.  Helpers exist only once the work counter has run dry, so a leader never takes another
+// query while it holds helpers: they are released when the leader itself goes idle.  The CTA retires when all four
+// warps are idle.
+constexpr uint32_t TEAM_BUSY = 0xfeu, TEAM_FREE = 0xffu;
+struct TeamShared {
+    unsigned long long job_bar[SEARCH_WARPS_PER_BLOCK];   // count 1: a job was posted for helper h
+    unsigned long long done_bar[SEARCH_WARPS_PER_BLOCK];  // count 1: helper h has written its distances
+    uint32_t owner[SEARCH_WARPS_PER_BLOCK];               // TEAM_BUSY | TEAM_FREE | warp index of the leader holding it
+    uint32_t done_parity[SEARCH_WARPS_PER_BLOCK];         // parity the next wait on done_bar[h] must observe (handed from holder to holder)
+    uint32_t n_idle;
+    struct Job { const float* qs; float qn; uint32_t n; uint32_t slot[32]; float dist[32]; } job[SEARCH_WARPS_PER_BLOCK];
+};
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {   // .release.cta
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {  // .acquire.cta; may give up after the hardware time limit
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+
+// leader: claim helpers if warps of this CTA have gone idle (at most its fair share of them)
+__device__ __forceinline__ void team_update(Ctx& c) {
+    TeamShared& ts = *c.ts;
+    const uint32_t idle = ld_volatile_shared(&ts.n_idle);
+    if (idle == 0) return;
+    const int have = __popc(*c.team & 0xfu);
+    const int want = max(1, (int)(idle / max(1u, (uint32_t)SEARCH_WARPS_PER_BLOCK - idle)));
+    if (have >= want) return;
+    uint32_t got = 0;
+    if (lane_id() == 0) {
+        const uint32_t me = threadIdx.x >> 5;
+        int n = have;
+        for (uint32_t h = 0; h < (uint32_t)SEARCH_WARPS_PER_BLOCK && n < want; ++h) {
+            if (h == me || ld_volatile_shared(&ts.owner[h]) != TEAM_FREE) continue;
+            if (atomicCAS(&ts.owner[h], TEAM_FREE, me) != TEAM_FREE) continue;
+            __threadfence_block();  // acquire: the previous holder wrote done_parity[h] before it freed h
+            got |= (1u << h) | ((ld_volatile_shared(&ts.done_parity[h]) & 1u) << (4 + h));
+            ++n;
+        }
+    }
+    got = __shfl_sync(FULL, got, 0);
+    *c.team |= got;
+}
+// leader going idle: hand its helpers back
+__device__ __forceinline__ void team_release(TeamShared& ts, uint32_t& team) {
+    __syncwarp();
+    if (lane_id() == 0) {
+        for (unsigned m = team & 0xfu; m; m &= m - 1) {
+            const int h = __ffs(m) - 1;
+            ts.done_parity[h] = (team >> (4 + h)) & 1u;
+            __threadfence_block();
+            *reinterpret_cast<volatile uint32_t*>(&ts.owner[h]) = TEAM_FREE;
+        }
+    }
+    team = 0;
+    __syncwarp();
+}
+
+// leader: share the live rows of one chunk out over the attached helpers.  Rows are split in order of rank, in whole
+// reduction groups: the leader keeps [0, per), the j-th helper takes [j * per, (j + 1) * per).  team_post hands the
+// helpers their slots and returns the mask of helpers used; team_collect waits for them and picks the distances up.
+__device__ __forceinline__ unsigned team_post(Ctx& c, unsigned lm, uint32_t s, int per) {
+    TeamShared& ts = *c.ts;
+    const int lane = lane_id();
+    const int n_live = __popc(lm);
+    const bool has = (lm >> lane) & 1;
+    const int rank = __popc(lm & ((1u << lane) - 1));
+    unsigned used = 0;
+    int j = 1;
+    for (unsigned m = *c.team & 0xfu; m && j * per < n_live; m &= m - 1, ++j) {
+        const int h = __ffs(m) - 1, lo = j * per, hi = min(n_live, lo + per);
+        TeamShared::Job& jb = ts.job[h];
+        if (has && rank >= lo && rank < hi) jb.slot[rank - lo] = s;
+        if (lane == 0) { jb.n = (uint32_t)(hi - lo); jb.qs = c.qs; jb.qn = c.qn; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_addr(&ts.job_bar[h]));
+        used |= 1u << h;
+    }
+    return used;
+}
+__device__ __forceinline__ float team_collect(Ctx& c, unsigned lm, unsigned used, int per, float d) {
+    TeamShared& ts = *c.ts;
+    const int lane = lane_id();
+    const int n_live = __popc(lm);
+    const bool has = (lm >> lane) & 1;
+    const int rank = __popc(lm & ((1u << lane) - 1));
+    int j = 1;
+    for (unsigned m = used; m; m &= m - 1, ++j) {
+        const int h = __ffs(m) - 1, lo = j * per, hi = min(n_live, lo + per);
+        const uint32_t bar = smem_addr(&ts.done_bar[h]);
+        while (!mbar_try_wait(bar, (*c.team >> (4 + h)) & 1u)) {}
+        *c.team ^= 1u << (4 + h);
+        if (has && rank >= lo && rank < hi) d = ts.job[h].dist[rank - lo];
+    }
+    __syncwarp();
+    return d;
+}
+
+// helper: serve jobs until every warp of the CTA is idle
+template <int KIND>
+__device__ __noinline__ void team_help(const SearchParams& p, TeamShared& ts, RowRing ring) {
+    const int lane = lane_id();
+    const uint32_t me = threadIdx.x >> 5;
+    const uint32_t jbar = smem_addr(&ts.job_bar[me]), dbar = smem_addr(&ts.done_bar[me]);
+    uint32_t par = 0;
+    for (;;) {
+        while (!mbar_try_wait(jbar, par))
+            if (ld_volatile_shared(&ts.n_idle) >= (uint32_t)SEARCH_WARPS_PER_BLOCK) return;
+        par ^= 1u;
+        TeamShared::Job& jb = ts.job[me];
+        Ctx c(p, ring);
+        c.qs = jb.qs; c.qn = jb.qn; c.tr = false;
+        const uint32_t n = jb.n;
+        const bool has = (uint32_t)lane < n;
+        const uint32_t s = has ? jb.slot[lane] : 0u;
+        RowsInFlight rf;
+        rows_begin<KIND>(c, __ballot_sync(FULL, has), s, rf);
+        const float d = rows_finish<KIND>(c, rf, s);
+        if (has) jb.dist[lane] = d;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dbar);
+    }
+}
+
 constexpr int MERGE_TILES = 8;  // heaps of up to 256 entries are merged through registers, larger ones tile by tile in place
 
 __device__ __forceinline__ u64 warp_min_u64(u64 v) {
@@ -353,6 +499,8 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
     const uint32_t* off = ix.off[level];
     const uint32_t* nbr = ix.nbr[level];
     const uint32_t* nbrx = level == 0 ? ix.nbr0x : nullptr;
+    const uint32_t xstride = ix.nbr0_stride;                 // 32, or 64: a full first line is followed by the second one
+    uint32_t cont_cs = 0;                                    // node whose fixed-stride list is being continued (csr_pos = 32, csr_end = xstride)
     const bool defer = nbrx && c.p.pass == 0 && c.p.defer && !linear && !c.p.no_trim;  // a linear scan pops nothing (reader.rs:683-705)
     uint32_t spec_cs = 0xffffffffu, spec_adj = 0xffffffffu;  // adjacency line requested ahead of its pop
     uint32_t csr_pos = 0, csr_end = 0;                       // rest of the CSR list being expanded
@@ -397,8 +545,9 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
                         c.cur_exp += 1;
                         if (can_cancel) ++c.polls;                 // the call that precedes this pop returned false
                         TR(c, TR_POP)
-                        uint32_t a = (cs == spec_cs) ? spec_adj : __ldg(&nbrx[(size_t)cs * FIXED_DEG + lane]);
+                        uint32_t a = (cs == spec_cs) ? spec_adj : __ldg(&nbrx[(size_t)cs * xstride + lane]);
                         heaps_stage_res(c, u, ef);                 // ... while the adjacency line is on its way
+                        if (xstride > FIXED_DEG && __shfl_sync(FULL, a, 31) != 0xffffffffu) { cont_cs = cs; csr_pos = FIXED_DEG; csr_end = xstride; }
                         valid = a != 0xffffffffu;
                         s = valid ? a : 0;
                         old = vis_issue(c, s, valid);
@@ -411,7 +560,7 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
                         have = true;
                         if (!c.overflow && c.q_len > 0) {          // the line of the pop after this one
                             spec_cs = ~(uint32_t)c.que[c.q_len - 1];
-                            spec_adj = __ldg(&nbrx[(size_t)spec_cs * FIXED_DEG + lane]);
+                            spec_adj = __ldg(&nbrx[(size_t)spec_cs * xstride + lane]);
                         } else {
                             spec_cs = 0xffffffffu;
                         }
@@ -439,11 +588,12 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
                     c.cur_exp += 1;
                     TR(c, TR_POP)
                     if (nbrx) {
-                        s = (cs == spec_cs) ? spec_adj : __ldg(&nbrx[(size_t)cs * FIXED_DEG + lane]);
+                        s = (cs == spec_cs) ? spec_adj : __ldg(&nbrx[(size_t)cs * xstride + lane]);
+                        if (xstride > FIXED_DEG && __shfl_sync(FULL, s, 31) != 0xffffffffu) { cont_cs = cs; csr_pos = FIXED_DEG; csr_end = xstride; }
                         // the entry now on top of the queue is popped next unless one of cs's neighbours beats it
                         if (c.q_len > 0) {
                             spec_cs = ~(uint32_t)c.que[c.q_len - 1];
-                            spec_adj = __ldg(&nbrx[(size_t)spec_cs * FIXED_DEG + lane]);
+                            spec_adj = __ldg(&nbrx[(size_t)spec_cs * xstride + lane]);
                         } else {
                             spec_cs = 0xffffffffu;
                         }
@@ -451,9 +601,13 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
                         csr_pos = __ldg(&off[cs]);
                         csr_end = __ldg(&off[cs + 1]);
                         if (csr_pos >= csr_end) continue;
+                        s = csr_pos + lane < csr_end ? __ldg(&nbr[csr_pos + lane]) : 0xffffffffu;
+                        csr_pos += 32;
                     }
-                }
-                if (!nbrx) {
+                } else if (nbrx) {   // the next line of a fixed-stride list longer than 32
+                    s = __ldg(&nbrx[(size_t)cont_cs * xstride + csr_pos + lane]);
+                    csr_pos += 32;
+                } else {
                     s = csr_pos + lane < csr_end ? __ldg(&nbr[csr_pos + lane]) : 0xffffffffu;
                     csr_pos += 32;
                 }
@@ -478,10 +632,22 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
         if (!lm) continue;
         c.cur_dist += __popc(lm);
         // ---- gather + distances ----
+        unsigned own = lm, helpers_used = 0;
+        int per = 32;
+        if (KIND == KIND_F32_WARP && c.ts) {
+            team_update(c);
+            const int H = __popc(*c.team & 0xfu), n_live = __popc(lm);
+            if (H && n_live > ROW_GROUP) {
+                per = (((n_live + H) / (H + 1)) + ROW_GROUP - 1) & ~(ROW_GROUP - 1);
+                helpers_used = team_post(c, lm, s, per);
+                own = __ballot_sync(FULL, live && __popc(lm & ((1u << lane) - 1)) < per);
+            }
+        }
         RowsInFlight rf;
-        rows_begin<KIND>(c, lm, s, rf);
+        rows_begin<KIND>(c, own, s, rf);
         TR(c, TR_POSTED)
-        const float dist = rows_finish<KIND>(c, rf, s);
+        float dist = rows_finish<KIND>(c, rf, s);
+        if (KIND == KIND_F32_WARP && helpers_used) dist = team_collect(c, lm, helpers_used, per, dist);
         const uint32_t bits = __float_as_uint(dist);
         if (l01) PH_ADD(c, PH_ROWS)
         if (mode != CH_LINEAR && c.p.pass == 0 && !c.p.no_trim && __ballot_sync(FULL, live && (bits >> 31))) { c.overflow = true; break; }
@@ -497,7 +663,7 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
             acc = live && (fill || dist < f_max);
             // an accepted point that beats the queue's current best is expanded very soon: start pulling its adjacency line
 #ifndef HB_NO_ADJ_PREFETCH
-            if (nbrx && acc && (c.q_len == 0 || bits <= (uint32_t)(c.que[c.q_len - 1] >> 32))) prefetch_l2(nbrx + (size_t)s * FIXED_DEG);
+            if (nbrx && acc && (c.q_len == 0 || bits <= (uint32_t)(c.que[c.q_len - 1] >> 32))) prefetch_l2(nbrx + (size_t)s * xstride);
 #endif
         }
         u.mode = mode; u.acc = acc; u.pf = pf; u.qskip = false; u.bits = bits; u.s = s;
@@ -608,10 +774,11 @@ __device__ __forceinline__ uint32_t next_unseen(const Ctx& c, uint32_t& wb) {
 }
 
 template <int KIND>
-__device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64* heap, float* qs, RowRing& ring) {
+__device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64* heap, float* qs, RowRing& ring, TeamShared* ts, uint32_t* team) {
     const DevIndex& ix = p.ix;
     const int lane = lane_id();
     Ctx c(p, ring);
+    c.ts = ts; c.team = team;
     c.res = heap; c.res_cap = p.res_cap; c.res_len = 0;
     c.que = heap + p.res_cap; c.q_cap = p.q_cap; c.q_len = 0;
     c.vis = p.visited + (size_t)slot_idx * p.vis_words;
@@ -805,14 +972,46 @@ __global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, KIND == KIND_F32_
         }
         __syncwarp();
     }
+    // helper state of the CTA (f32 ring kernel only)
+    constexpr bool TEAM = KIND == KIND_F32_WARP;
+    __shared__ TeamShared team_shared;
+    TeamShared* ts = nullptr;
+    uint32_t team = 0;
+    if (TEAM && p.team) {
+        ts = &team_shared;
+        if (threadIdx.x < SEARCH_WARPS_PER_BLOCK) {
+            mbar_init(smem_addr(&ts->job_bar[threadIdx.x]), 1);
+            mbar_init(smem_addr(&ts->done_bar[threadIdx.x]), 1);
+            ts->owner[threadIdx.x] = TEAM_BUSY;
+            ts->done_parity[threadIdx.x] = 0;
+            if (threadIdx.x == 0) ts->n_idle = 0;
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
     const uint32_t n_work = p.pass == 0 ? p.n_work : *p.n_overflow;
+    // the first n_static queries are handed out by position — warp w of CTA b starts with query w * gridDim + b, so a
+    // batch smaller than the grid spreads over all CTAs (and leaves every CTA helpers) — the rest by the counter
+    unsigned long long w = (unsigned long long)warp_in_block * gridDim.x + blockIdx.x;
+    bool by_position = w < p.n_static;
     for (;;) {
-        unsigned long long w = 0;
-        if (lane_id() == 0) w = atomicAdd(p.work_counter + p.pass, 1ull);
-        w = __shfl_sync(FULL, w, 0);
+        if (!by_position) {
+            if (lane_id() == 0) w = p.n_static + atomicAdd(p.work_counter + p.pass, 1ull);
+            w = __shfl_sync(FULL, w, 0);
+        }
+        by_position = false;
         if (w >= n_work) break;
         uint64_t qi = p.pass == 0 ? w : p.overflow_list[w];
-        run_query<KIND>(p, qi, slot_idx, heap, qs, ring);
+        run_query<KIND>(p, qi, slot_idx, heap, qs, ring, ts, &team);
+    }
+    if (TEAM && ts) {
+        team_release(*ts, team);
+        if (lane_id() == 0) {
+            *reinterpret_cast<volatile uint32_t*>(&ts->owner[warp_in_block]) = TEAM_FREE;
+            atomicAdd(&ts->n_idle, 1u);
+        }
+        __syncwarp();
+        team_help<KIND>(p, *ts, ring);
     }
 }
 
@@ -1061,12 +1260,16 @@ hb_status launch_search(const SearchParams& fast, const SearchParams& slow, int 
     if (fast.res_cap) {
         cudaMemsetAsync(fast.n_overflow, 0, sizeof(uint32_t), stream);
         size_t smem = search_smem_per_warp(fast) * wpb;
-        uint64_t need = ((uint64_t)fast.n_work + wpb - 1) / wpb;
+        // a batch smaller than the resident warps: one CTA per query while CTAs last (its other warps become helpers)
+        const bool team = variant_of(fast) == KIND_F32_WARP && fast.team;
+        uint64_t need = team ? (uint64_t)fast.n_work : ((uint64_t)fast.n_work + wpb - 1) / wpb;
         int blocks = (uint64_t)blocks_fast > need ? (int)need : blocks_fast;
         if (blocks < 1) blocks = 1;
+        SearchParams fp = fast;
+        fp.n_static = (uint32_t)std::min<uint64_t>(fast.n_work, (uint64_t)blocks * wpb);
         static const bool dbg = getenv("HB_DEBUG_LAUNCH") != nullptr;
         if (dbg) fprintf(stderr, "[hb] search launch: kind %d, %d CTAs x %d threads, %zu B shared memory per CTA, res_cap %u q_cap %u\n", variant_of(fast), blocks, wpb * 32, smem, fast.res_cap, fast.q_cap);
-        kernel_for(variant_of(fast))<<<blocks, wpb * 32, smem, stream>>>(fast);
+        kernel_for(variant_of(fast))<<<blocks, wpb * 32, smem, stream>>>(fp);
         ++g_launches;
     } else {
         uint32_t n = fast.n_work;

@@ -153,7 +153,13 @@ hb_status decode_kv(hb_index* ix, const uint8_t* key, size_t klen, const uint8_t
             if (ix->have_metadata) {  // the usual order: no staging copy, the row lands in its slot
                 const std::vector<uint32_t>& mi = ix->meta_items;
                 auto it = std::lower_bound(mi.begin(), mi.end(), item);
-                if (it == mi.end() || *it != item) return HB_OK;  // not listed in the metadata: never read by the Reader
+                if (it == mi.end() || *it != item) {
+                    // not listed in the metadata: never read by the Reader (a pending `add_item`, which also leaves an Updated
+                    // stone => NeedBuild); kept aside for hb_index_build_graph, whose item set is every Item node present
+                    // (writer.rs:539-553: (updated | indexed) - deleted)
+                    ix->kv_items[item].assign(val + 1, val + vlen);
+                    return HB_OK;
+                }
                 size_t s = (size_t)(it - mi.begin()), rb = natural_row_bytes(ix->metric, ix->meta_dims);
                 if (!ix->direct_rows) {
                     ix->host_rows.assign(mi.size() * rb, 0);
@@ -244,6 +250,68 @@ hb_status build_host_snapshot_from_kv(hb_index* ix) {
     ix->kv_items.clear();
     ix->kv_links.clear();
     std::vector<uint8_t>().swap(ix->row_seen);
+    return HB_OK;
+}
+
+// The item set of a (re)build — `Writer::build`, writer.rs:539-553: `(updated | indexed) - deleted`.  `add_item` writes the
+// Item node and `del_item` removes it (writer.rs:483-495), so that set is exactly the Item nodes present in the database:
+// the rows decoded against the stored metadata (row_seen) plus the ones kept aside in kv_items.  The stored `items`
+// bitmap, links, entry points and Updated stones of a previous build are not used: the graph is built from scratch.
+hb_status build_host_items_for_build(hb_index* ix, uint32_t dims_opt) {
+    uint32_t dims = dims_opt;
+    if (ix->have_metadata) {
+        if (ix->meta_distance != hb_metric_name(ix->metric)) {
+            set_error("Internal error: unmatching distance: expected `%s`, received `%s`", ix->meta_distance.c_str(), hb_metric_name(ix->metric));
+            return HB_EUNMATCHING_DISTANCE;
+        }
+        if (dims_opt && dims_opt != ix->meta_dims) { set_error("hb_index_build_graph: dimensions %u given, the metadata says %u", dims_opt, ix->meta_dims); return HB_EDIM; }
+        dims = ix->meta_dims;
+    }
+    if (!dims) { set_error("hb_index_build_graph: the database has no metadata, pass hb_build_opts.dimensions"); return HB_EMISSING_METADATA; }
+    const size_t rb = natural_row_bytes(ix->metric, dims), hs = header_size(ix->metric);
+    std::vector<std::pair<uint32_t, int64_t>> src;  // (id, slot in the direct rows or -1 = kv_items), ascending ids
+    if (ix->direct_rows)
+        for (size_t s = 0; s < ix->meta_items.size(); ++s)
+            if (ix->row_seen[s]) src.push_back({ix->meta_items[s], (int64_t)s});
+    const size_t n_direct = src.size();
+    for (auto& kv : ix->kv_items) src.push_back({kv.first, -1});
+    std::inplace_merge(src.begin(), src.begin() + n_direct, src.end());
+    const size_t n = src.size();
+    std::vector<uint8_t> rows(n * rb, 0);
+    std::vector<float> hdr(n, 0.0f);
+    std::vector<uint32_t> ids(n);
+    for (size_t i = 0; i < n; ++i) {
+        ids[i] = src[i].first;
+        if (i && ids[i] == ids[i - 1]) { set_error("item %u appears twice", ids[i]); return HB_EFORMAT; }
+        if (src[i].second >= 0) {
+            std::memcpy(rows.data() + i * rb, ix->host_rows.data() + (size_t)src[i].second * rb, rb);
+            hdr[i] = ix->host_hdr[(size_t)src[i].second];
+        } else {
+            const std::vector<uint8_t>& v = ix->kv_items[ids[i]];
+            if (v.size() < hs + rb) { set_error("item %u: vector shorter than the index dimensions", ids[i]); return HB_EFORMAT; }
+            if (hs == 4) std::memcpy(&hdr[i], v.data(), 4);
+            std::memcpy(rows.data() + i * rb, v.data() + hs, rb);
+        }
+    }
+    ix->dims = dims;
+    ix->ids.swap(ids);
+    ix->host_row_bytes = rb;
+    ix->host_rows.swap(rows);
+    ix->host_hdr.swap(hdr);
+    ix->layers.clear();
+    ix->eps.clear();
+    ix->max_level = 0;
+    ix->kv_items.clear();
+    ix->kv_links.clear();
+    ix->direct_rows = false;
+    std::vector<uint8_t>().swap(ix->row_seen);
+    ix->meta_distance = hb_metric_name(ix->metric);
+    ix->meta_dims = dims;
+    ix->meta_items = ix->ids;
+    ix->meta_eps.clear();
+    ix->meta_max_level = 0;
+    ix->have_metadata = true;
+    ix->need_build = false;  // building is what the caller is about to do
     return HB_OK;
 }
 

@@ -6,7 +6,9 @@ Differences from the Rust API, all forced by the snapshot design:
     heed cursor over the LMDB read transaction yields — instead of `(&RoTxn, index, Database<D>)`;
     the transaction is read once, queries need no `rtxn`.
   * batched `by_vectors` / `by_items` are added; `by_vector` / `by_item` are the single-query forms.
-  * cancellation closures cannot cross the ABI: `did_cancel` is always False.
+  * cancellation closures cannot cross the ABI as such: a `CancelToken` (a device flag any host thread may trip) or a
+    poll count stand in for `cancel_fn`; `Searched.did_cancel()` reports it like the reference.
+  * `Reader.replicate(devices)` copies the snapshot to further GPUs; every batched call then partitions its batch.
 """
 import ctypes as C
 import os
@@ -453,6 +455,17 @@ class Reader:
             lib.hb_index_free(h)
             raise
         return cls(h, d, index, device)
+
+    def replicate(self, devices):
+        """Copy the snapshot to further GPUs (hb_index_replicate): one `by_vectors` / `by_items` call then searches
+        contiguous nq / n_devices slices of its batch on every device at once."""
+        devs = np.ascontiguousarray(list(devices), dtype=np.int32)
+        _check(L.lib().hb_index_replicate(self._h, _ptr(devs), len(devs)))
+        return self
+
+    def devices(self):
+        n = L.lib().hb_index_n_devices(self._h)
+        return [L.lib().hb_index_device(self._h, i) for i in range(n)]
 
     # accessors — reader.rs:545-606
     def dimensions(self):

@@ -85,6 +85,11 @@ class ShardedSearcher:
         lens = torch.empty((nq,), dtype=torch.int32, device=dev)
         self.reader.search_device(d_q.data_ptr(), nq, count, max(ef, count), ids.data_ptr(), dist.data_ptr(), lens.data_ptr(),
                                   None, stream.cuda_stream)
+        # the kernel zeroes the slots past out_len (its output is a function of its inputs): re-pad them with the merge
+        # sentinel, or a shard that finds fewer than `count` hits would contribute bogus (id 0, distance 0) entries
+        pad = torch.arange(count, device=dev, dtype=torch.int32)[None, :] >= (lens & 0x7fffffff)[:, None]
+        ids.masked_fill_(pad, -1)
+        dist.masked_fill_(pad, float("inf"))
         g_ids = torch.empty((self.world * nq, count), dtype=torch.int32, device=dev)   # == [world][nq][count]
         g_dist = torch.empty((self.world * nq, count), dtype=torch.float32, device=dev)
         self.dist.all_gather_into_tensor(g_ids, ids, group=self.group)

@@ -101,7 +101,8 @@ hb_status hb_index_load(hb_index*, const char* path);
  * `robust_prune` and `add_link` in both directions run as kernels — and leaves per-layer links, entry points and
  * max_level in the index.  hb_index_finalize then uploads it for searching; hb_index_export_kv hands it back in the
  * reference's on-disk encoding.  Like the reference's rayon build the result depends on insertion interleaving: a
- * valid hannoy graph of the same quality, not a bit-copy of a CPU build.  M <= 32, M0 <= 32.
+ * valid hannoy graph of the same quality, not a bit-copy of a CPU build.  M <= 32, M0 <= 64 (the reference's bindings
+ * instantiate (16,32), (24,48) and (32,64), src/python.rs:280).
  * stats_out (optional): u64[8] = batches, kernel launches, items, max_level, reverse links dropped because more than 32
  * arrived for one node in one batch, candidate walks cut short, milliseconds in the batch loop (kernels), milliseconds in
  * the whole call (row upload, kernels, download and CSR). */
@@ -133,6 +134,17 @@ hb_status hb_index_from_arrays(hb_index*, uint32_t dims, const uint32_t* ids, ui
  * roaring edge lists into per-layer CSR over dense ranks, repacks rows into the 16-byte aligned
  * device layout and uploads everything to `device`.  After this the index is immutable. */
 hb_status hb_index_finalize(hb_index*, int device);
+
+/* Replicas on further GPUs (the reference's `Reader` is `Send + Sync` and is shared by the threads of a
+ * rayon pool, src/parallel.rs:18-38 — here the "threads" are devices).  hb_index_replicate copies the finalized device
+ * snapshot to each of `devices` (device-to-device); hb_index_finalize_replicated = hb_index_finalize(devices[0]) +
+ * hb_index_replicate(devices + 1, n_dev - 1).  From then on ONE hb_search_by_vector / hb_search_by_item call partitions
+ * its batch into contiguous nq / n_devices slices, one host thread + stream per device, no collective; results are
+ * identical to the single-device call.  The *_device entry points keep running on device 0 of the index. */
+hb_status hb_index_replicate(hb_index*, const int* devices, int n_dev);
+hb_status hb_index_finalize_replicated(hb_index*, const int* devices, int n_dev);
+int hb_index_n_devices(const hb_index*);
+int hb_index_device(const hb_index*, int i);   /* CUDA ordinal of the i-th copy, -1 if out of range */
 
 void hb_index_free(hb_index*);
 
@@ -233,20 +245,6 @@ void hb_shard_group_free(hb_shard_group*);
 
 /* number of kernel launches issued by this library in this process (for bench gpu_launches) */
 uint64_t hb_launch_count(void);
-
-/* Engine tuning knob (no reference counterpart; never changes results): e.g. "ring_bytes" (shared-memory
- * bytes of rows in flight per query warp), "blocks_per_sm", "fixed_adjacency", "touched_cap".  Takes
- * effect for indexes finalized / workspaces created afterwards; the environment variable HB_<KEY> is the
- * default. */
-hb_status hb_tune(const char* key, int value);
-
-/* Development aid: cycles per phase of the search kernel summed over all queries since the last call
- * (stage, upper layers, adjacency wait, visited filter, row gather+distance, heap update, tail, total).
- * All zero unless the library was built with -DHB_PHASES. */
-void hb_debug_phases(uint64_t* out8);
-/* Development aid: event trace (clock64 << 8 | event id) of one query warp since the last call; returns the
- * number of records copied.  Always 0 unless the library was built with -DHB_TRACE. */
-uint32_t hb_debug_trace(uint64_t* out, uint32_t cap);
 
 const char* hb_last_error(void);
 

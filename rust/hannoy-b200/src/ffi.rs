@@ -77,7 +77,8 @@ extern "C" {
     ) -> hb_status;
     pub fn hb_exact_knn(ix: *const hb_index, q: *const f32, nq: u64, dims: u32, k: u32, out_ids: *mut u32, out_dist: *mut f32) -> hb_status;
     pub fn hb_last_error() -> *const c_char;
-    pub fn hb_tune(key: *const c_char, value: c_int) -> hb_status;
+    pub fn hb_index_replicate(ix: *mut hb_index, devices: *const c_int, n_dev: c_int) -> hb_status;
+    pub fn hb_index_n_devices(ix: *const hb_index) -> c_int;
     #[allow(dead_code)]
     pub fn hb_search_by_vector_device(
         ix: *const hb_index, d_q: *const f32, nq: u64, count: u32, ef: u32, d_out_ids: *mut u32, d_out_dist: *mut f32,

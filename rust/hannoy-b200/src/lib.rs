@@ -119,11 +119,13 @@ impl<D: Distance> GpuReader<D> {
         let this = GpuReader { raw, dimensions, device, _marker: PhantomData };
         let raw_db = database.remap_types::<Bytes, Bytes>();
         let mut stones = Vec::new();
+        let mut stale_links: Vec<Vec<u8>> = Vec::new();
         for kv in raw_db.prefix_iter(wtxn, &index.to_be_bytes())? {
             let (k, v) = kv?;
             match k[2] {
                 3 => check(unsafe { ffi::hb_index_push_kv(this.raw, k.as_ptr(), k.len(), v.as_ptr(), v.len()) }, (0, 0))?, // Item nodes
                 1 => stones.push(k.to_vec()),                                                                          // Updated
+                2 => stale_links.push(k.to_vec()),                                                                     // Links of the previous build
                 _ => {}
             }
         }
@@ -136,6 +138,11 @@ impl<D: Distance> GpuReader<D> {
         }
         let mut pairs: Vec<(Vec<u8>, Vec<u8>)> = Vec::new();
         check(unsafe { ffi::hb_index_export_kv(this.raw, 0, collect, &mut pairs as *mut _ as *mut _) }, (0, 0))?;
+        // the graph is rebuilt from scratch: links of items that no longer exist (or of layers an item no longer reaches)
+        // must not survive (writer.rs:577 `delete_links_from_db`)
+        for k in &stale_links {
+            raw_db.delete(wtxn, k)?;
+        }
         for (k, v) in &pairs {
             raw_db.put(wtxn, k, v)?;
         }
@@ -146,6 +153,14 @@ impl<D: Distance> GpuReader<D> {
         Ok(this)
     }
 
+    /// Copies the HBM-resident snapshot to further GPUs; `by_vectors` then partitions every batch into contiguous
+    /// slices, one per device (hannoy shares one `Reader` between the threads of a rayon pool, src/parallel.rs:18-38).
+    pub fn replicate(&mut self, devices: &[i32]) -> Result<()> {
+        check(unsafe { ffi::hb_index_replicate(self.raw, devices.as_ptr(), devices.len() as i32) }, (0, 0))
+    }
+    pub fn n_devices(&self) -> usize {
+        unsafe { ffi::hb_index_n_devices(self.raw) as usize }
+    }
     pub fn dimensions(&self) -> usize {
         self.dimensions
     }

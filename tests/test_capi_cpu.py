@@ -27,8 +27,11 @@ def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "hannoy_b200.h")).read()
     declared = set(re.findall(r"\b(hb_[a-z_0-9]+)\s*\(", hdr))
     assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
+    dev_hdr = open(os.path.join(ROOT, "include", "hannoy_b200_dev.h")).read()
+    dev_declared = set(re.findall(r"\b(hb_[a-z_0-9]+)\s*\(", dev_hdr))
+    assert dev_declared == set(L.DEV_EXPORTS), dev_declared ^ set(L.DEV_EXPORTS)
     lib = C.CDLL(L.SO_PATH)
-    for name in declared:
+    for name in declared | dev_declared:
         assert hasattr(lib, name), name
 
 
