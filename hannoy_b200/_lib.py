@@ -28,6 +28,7 @@ EXPORTS = [
     "hb_index_max_level", "hb_index_version", "hb_index_item_ids", "hb_index_contains_item", "hb_index_item_vector",
     "hb_search_by_vector", "hb_search_by_item", "hb_search_by_vector_device", "hb_exact_knn", "hb_merge_topk_device",
     "hb_launch_count", "hb_last_error", "hb_index_replicate", "hb_index_finalize_replicated", "hb_index_n_devices", "hb_index_device",
+    "hb_index_n_layers", "hb_index_entry_points", "hb_index_layer_csr",
     "hb_cancel_token_create", "hb_cancel_token_cancel", "hb_cancel_token_reset", "hb_cancel_token_is_cancelled",
     "hb_cancel_token_free", "hb_shard_group_create", "hb_shard_group_connect", "hb_search_sharded_device", "hb_shard_group_free",
 ]
@@ -74,6 +75,8 @@ def lib():
         "hb_index_finalize": (i32, [vp, i32]), "hb_index_free": (None, [vp]),
         "hb_index_replicate": (i32, [vp, vp, i32]), "hb_index_finalize_replicated": (i32, [vp, vp, i32]),
         "hb_index_n_devices": (i32, [vp]), "hb_index_device": (i32, [vp, i32]),
+        "hb_index_n_layers": (u32, [vp]), "hb_index_entry_points": (u32, [vp, vp, u32]),
+        "hb_index_layer_csr": (i32, [vp, u32, vp, vp, u64, C.POINTER(u64)]),
         "hb_index_dimensions": (u32, [vp]), "hb_index_n_items": (u64, [vp]),
         "hb_index_n_entry_points": (u32, [vp]), "hb_index_max_level": (u32, [vp]),
         "hb_index_version": (i32, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),

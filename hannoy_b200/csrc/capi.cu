@@ -542,6 +542,29 @@ uint64_t hb_index_item_ids(const hb_index* ix, uint32_t* out, uint64_t cap) {
     return ix->ids.size();
 }
 int hb_index_contains_item(const hb_index* ix, uint32_t item) { return ix && slot_of(ix, item) >= 0; }
+uint32_t hb_index_n_layers(const hb_index* ix) { return ix ? (uint32_t)ix->layers.size() : 0; }
+uint32_t hb_index_entry_points(const hb_index* ix, uint32_t* out, uint32_t cap) {
+    if (!ix) return 0;
+    for (size_t i = 0; i < ix->eps.size() && i < cap && out; ++i) out[i] = ix->ids[ix->eps[i]];
+    return (uint32_t)ix->eps.size();
+}
+hb_status hb_index_layer_csr(const hb_index* ix, uint32_t layer, uint64_t* offsets, uint32_t* nbr_ids, uint64_t cap, uint64_t* nnz_out) {
+    if (!ix) return HB_EINVAL;
+    if (layer >= ix->layers.size()) { set_error("hb_index_layer_csr: the index has %zu layers", ix->layers.size()); return HB_EINVAL; }
+    const HostLayer& hl = ix->layers[layer];
+    const size_t n = ix->ids.size();
+    const uint64_t nnz = hl.off.size() == n + 1 ? hl.off[n] : 0;
+    if (nnz_out) *nnz_out = nnz;
+    if (offsets) {
+        if (hl.off.size() == n + 1) std::copy(hl.off.begin(), hl.off.end(), offsets);
+        else std::fill(offsets, offsets + n + 1, 0);
+    }
+    if (nbr_ids) {
+        if (cap < nnz) { set_error("hb_index_layer_csr: room for %llu neighbours, the layer has %llu", (unsigned long long)cap, (unsigned long long)nnz); return HB_EINVAL; }
+        for (uint64_t e = 0; e < nnz; ++e) nbr_ids[e] = ix->ids[hl.nbr[e]];
+    }
+    return HB_OK;
+}
 hb_status hb_index_item_vector(const hb_index* ix, uint32_t item, float* out) {
     if (!ix || !out) return HB_EINVAL;
     int64_t s = slot_of(ix, item);

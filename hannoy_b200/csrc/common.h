@@ -229,7 +229,7 @@ void layout_row(int kind, uint32_t dims, const uint8_t* natural, uint8_t* out);
 int kind_for(hb_metric m, uint32_t dims);
 // search.cu
 constexpr int SEARCH_WARPS_PER_BLOCK = 4;
-constexpr int SEARCH_MAX_SMEM = 226 * 1024;  // per SM (227 KB usable, 1 KB reserved per resident CTA)
+constexpr int SEARCH_MAX_SMEM = 224 * 1024;  // dynamic shared memory a search CTA may ask for: 227 KB per CTA less the kernel's static TeamShared block
 hb_status launch_search(const SearchParams& fast, const SearchParams& slow, int blocks_fast, int blocks_slow, void* stream);
 size_t search_smem_per_warp(const SearchParams& p);
 int search_blocks_per_sm(const SearchParams& p);  // resident CTAs per SM for these parameters

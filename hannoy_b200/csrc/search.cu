@@ -1233,7 +1233,9 @@ static void set_kernel_attrs() {
     static bool attr_set = false;
     if (!attr_set) {
         for (int k = 0; k < 4; ++k)
-            cudaFuncSetAttribute(kernel_for(k), cudaFuncAttributeMaxDynamicSharedMemorySize, SEARCH_MAX_SMEM);
+            if (cudaFuncSetAttribute(kernel_for(k), cudaFuncAttributeMaxDynamicSharedMemorySize, SEARCH_MAX_SMEM) != cudaSuccess) {
+                fprintf(stderr, "[hb] cudaFuncSetAttribute(MaxDynamicSharedMemorySize = %d) failed for search kernel %d: %s\n", SEARCH_MAX_SMEM, k, cudaGetErrorString(cudaGetLastError()));
+            }
         attr_set = true;
     }
 }

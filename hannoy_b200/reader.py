@@ -489,6 +489,25 @@ class Reader:
     def index(self):
         return self._index
 
+    def entry_points(self):
+        n = L.lib().hb_index_entry_points(self._h, None, 0)
+        out = np.zeros(n, np.uint32)
+        L.lib().hb_index_entry_points(self._h, _ptr(out), n)
+        return out
+
+    def layers(self):
+        """[(offsets u64[n+1], neighbour item ids u32[nnz])] per layer — the shape `from_arrays` takes (hb_index_layer_csr)."""
+        out = []
+        n = self.n_items()
+        for l in range(L.lib().hb_index_n_layers(self._h)):
+            nnz = C.c_uint64()
+            _check(L.lib().hb_index_layer_csr(self._h, l, None, None, 0, C.byref(nnz)))
+            off = np.zeros(n + 1, np.uint64)
+            nbr = np.zeros(nnz.value, np.uint32)
+            _check(L.lib().hb_index_layer_csr(self._h, l, _ptr(off), _ptr(nbr), nnz.value, None))
+            out.append((off, nbr))
+        return out
+
     def version(self):
         a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
         _check(L.lib().hb_index_version(self._h, C.byref(a), C.byref(b), C.byref(c)))

@@ -158,6 +158,15 @@ hb_status hb_index_version(const hb_index*, uint32_t* major, uint32_t* minor, ui
 uint64_t hb_index_item_ids(const hb_index*, uint32_t* out, uint64_t cap);
 /* Reader::contains_item (reader.rs:595-601) */
 int hb_index_contains_item(const hb_index*, uint32_t item);
+/* The graph of the snapshot as flat arrays — the inverse of hb_index_from_arrays, what iterating `Links` nodes
+ * (src/node.rs:162-165, reader.rs:966-976 get_links) gives: number of layers; entry-point item ids in metadata order
+ * (returns how many there are, copies min(cap, that)); one layer as CSR: offsets (n+1, may be NULL), neighbour ITEM
+ * IDS ascending inside each list (room for `cap` entries, may be NULL), *nnz_out = edges of the layer.  Lets a host-side
+ * reader (the oracle, a CPU hannoy) take over a graph that hb_index_build_graph built without going through
+ * per-pair export callbacks. */
+uint32_t hb_index_n_layers(const hb_index*);
+uint32_t hb_index_entry_points(const hb_index*, uint32_t* out, uint32_t cap);
+hb_status hb_index_layer_csr(const hb_index*, uint32_t layer, uint64_t* offsets, uint32_t* nbr_ids, uint64_t cap, uint64_t* nnz_out);
 /* Reader::item_vector (reader.rs:581-587): decoded f32 vector truncated to `dimensions`; HB_EINVAL if absent */
 hb_status hb_index_item_vector(const hb_index*, uint32_t item, float* out);
 

@@ -47,7 +47,9 @@ def test_wide_layer0_lists_match_oracle(metric, n, dims, kind, M, M0, efc):
         for polls in (1, 4, 30):   # cancellation polls are counted per pop, not per chunk of a long list
             want = db.search_by_vector(q[:16], 10, ef=64, cancel_after=polls, counters=True)
             got = rd.nns(10).ef_search(64).with_cancellation(polls).by_vectors_raw(q[:16], counters=True)
+            got = (got[0], got[1], got[2] & 0x7fffffff, got[3])   # bit 31 = did_cancel
             assert_same(got, want, f"cancel after {polls} polls, {metric} M0={M0}")
+            assert_counters_same(got[3], want[3], f"cancel after {polls} polls, {metric} M0={M0}")
 
 
 @pytest.mark.parametrize("metric,dims", [("cosine", 768), ("euclidean", 128), ("cosine", 100)])
