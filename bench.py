@@ -685,6 +685,23 @@ def run_sharded(args, w, rank, world, local_rank, dev, use_dist, threads, log, s
         dist.init_process_group("nccl" if dev.type == "cuda" else "gloo", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1,
                                 **({"device_id": dev} if dev.type == "cuda" else {}))
     n, dims, nq, k, ef = w["n"], w["dims"], w["nq"], w["k"], w["efs"][0]
+    # host memory: every rank holds its shard three times on the host while it is set up (the generated array, the snapshot
+    # inside the library, the oracle's copy for the parity check): shrink the shards rather than take the box down
+    n_asked, ram_note = n, None
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+        n_fit = int(avail * 0.6 / max(world, 1) / (dims * 4 * 3.2))
+        if n_fit < n:
+            n = max(100_000, n_fit // 100_000 * 100_000)
+            ram_note = f"shards cut from {n_asked} to {n} items: the host has {avail / 2**30:.0f} GiB free for {world} ranks"
+            log(ram_note)
+    except Exception:
+        pass
+    if use_dist or dist.is_initialized():   # every rank must use the same shard size
+        t = torch.tensor([n], device=dev, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        n = int(t.item())
     t0 = time.time()
     x = gen_vectors(w["gen"], n, dims, w["seed"] + 100 * rank, dev).cpu().numpy()
     q = gen_vectors(w["gen"], nq, dims, w["seed"] + 1, dev)
@@ -760,7 +777,8 @@ def run_sharded(args, w, rank, world, local_rank, dev, use_dist, threads, log, s
         line = {"metric": "QPS (batched, id-sharded index)", "value": round(nq / (ms_fused / 1e3), 1), "unit": "queries/s", "n_gpus": world,
                 "steps": steps, "warmup": warm, "ms_per_step": round(ms_fused, 4), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": w["desc"], "metric": w["metric"], "items_per_shard": n, "n_shards": world, "total_items": n * world, "dims": dims,
+                "config": {"workload": w["desc"], "metric": w["metric"], "items_per_shard": n, "items_per_shard_asked": n_asked, "host_ram_note": ram_note,
+                           "n_shards": world, "total_items": n * world, "dims": dims,
                            "batch_queries": nq, "k": k, "ef_search": ef, "graphs": how,
                            "exchange": "fused into the search kernel epilogue (peer-memory stores over NVLink) + merge kernel",
                            "cache": "inputs larger than L2"},

@@ -96,7 +96,11 @@ def lib():
         "hb_tune": (i32, [C.c_char_p, i32]), "hb_debug_phases": (None, [vp]), "hb_debug_trace": (u32, [vp, u32]), "hb_launch_count": (u64, []), "hb_last_error": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
-        fn = getattr(L, name)
+        fn = getattr(L, name, None)
+        if fn is None:
+            if _VARIANT:   # dev builds of older sources may lack newer entry points
+                continue
+            raise ImportError(f"{SO_PATH} lacks {name}: rebuild it with `python -m hannoy_b200.build`")
         fn.restype, fn.argtypes = res, args
     _lib = L
     return L

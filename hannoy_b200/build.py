@@ -12,8 +12,8 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["capi.cu", "search.cu", "exact.cu", "build.cu", "snapshot.cpp", "lmdb_walk.cpp"]
-HEADERS = ["common.h", "dist.cuh", "sorted.cuh", "ring.cuh", os.path.join("..", "..", "include", "hannoy_b200.h")]
+SOURCES = ["capi.cu", "search.cu", "exact.cu", "exact_tc.cu", "build.cu", "snapshot.cpp", "lmdb_walk.cpp"]
+HEADERS = ["common.h", "dist.cuh", "sorted.cuh", "ring.cuh", "stage.cuh", os.path.join("..", "..", "include", "hannoy_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -22,7 +22,7 @@ FLAGS = [
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function",
 ]
 VARIANTS = {"": [], "phases": ["-DHB_PHASES"], "trace": ["-DHB_TRACE"], "rg2": ["-DHB_ROW_GROUP=2"],
-             "bin5": ["-DHB_MIN_BLOCKS_BIN=5"], "bin6": ["-DHB_MIN_BLOCKS_BIN=6"], "bin8": ["-DHB_MIN_BLOCKS_BIN=8"]}
+             "late": ["-DHB_EARLY_ROWS=0"], "bin5": ["-DHB_MIN_BLOCKS_BIN=5"], "bin6": ["-DHB_MIN_BLOCKS_BIN=6"], "bin8": ["-DHB_MIN_BLOCKS_BIN=8"]}
 
 
 def out_path(variant=""):

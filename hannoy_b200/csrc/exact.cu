@@ -1,69 +1,20 @@
 // exact.cu — exact k-NN over every item (recall ground truth) and the per-shard top-k merge.
 // The exact scan uses the same distance routines as the graph walk, so its distances are bit-identical
-// to the search kernel's and to the reference's (dist.cuh).  A tensor-core GEMM is deliberately not used
-// here: bf16/tf32 products would make the "exact" ground truth approximate.
+// to the search kernel's and to the reference's (dist.cuh).  For Cosine / Euclidean rows of 32+ dimensions the scan is
+// preceded by a tf32 tensor-core GEMM that prunes the items to a provably sufficient shortlist (exact_tc.cu); the
+// distances that are ranked are always the bit-exact ones computed here.
 #include <cfloat>
 
 #include "dist.cuh"
 #include "sorted.cuh"
+#include "stage.cuh"
 
 namespace hb {
 
+hb_status launch_exact_knn_scan(const DevIndex& ix, const float* d_q, uint64_t nq, uint32_t k, uint32_t* d_ids, float* d_dist, void* stream);
+
 constexpr int EX_WARPS = 8;
 constexpr int EX_TQ = 8;  // queries per block
-
-// stage one raw f32 query into the device row layout (same code path as search.cu:stage_query, by_vector)
-__device__ void ex_stage_query(const DevIndex& ix, const float* src, float* qs, float* qn_out) {
-    const int lane = lane_id();
-    const uint32_t words16 = ix.row_stride / 16;
-    uint4* q16 = reinterpret_cast<uint4*>(qs);
-    for (uint32_t i = lane; i < words16; i += 32) q16[i] = make_uint4(0, 0, 0, 0);
-    __syncwarp();
-    if (ix.kind == KIND_F32_WARP) {
-        uint32_t main = ix.dims - ix.tail;
-        for (uint32_t e = lane; e < ix.dims; e += 32) {
-            float v = __ldg(src + e);
-            if (e < main) { uint32_t blk = e >> 5, j = e & 31; qs[(blk >> 2) * 128 + j * 4 + (blk & 3)] = v; }
-            else qs[ix.tail_off + (e - main)] = v;
-        }
-    } else if (ix.kind == KIND_F32_LANE) {
-        for (uint32_t e = lane; e < ix.dims; e += 32) qs[e] = __ldg(src + e);
-    } else {
-        uint32_t* q32 = reinterpret_cast<uint32_t*>(qs);
-        for (uint32_t base = 0; base < ix.dims; base += 32) {
-            uint32_t e = base + lane;
-            bool bit = false;
-            if (e < ix.dims) {
-                uint32_t u = __float_as_uint(__ldg(src + e));
-                bit = (ix.metric == HB_HAMMING) ? (u < 0x80000000u && u > 0u) : ((u >> 31) == 0);
-            }
-            unsigned w = __ballot_sync(FULL, bit);
-            if (lane == 0) q32[base >> 5] = w;
-        }
-    }
-    __syncwarp();
-    float qn = 0.0f;
-    if (ix.metric == HB_COSINE) {
-        float dot;
-        if (ix.kind == KIND_F32_WARP) {
-            float acc = 0.0f;
-            const float4* q4 = reinterpret_cast<const float4*>(qs);
-            for (uint32_t ch = 0; ch < ix.n_chunks; ++ch) {
-                float4 v = q4[ch * 32 + lane];
-                acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
-            }
-            dot = warp_hsum_avx(acc);
-            for (uint32_t e = 0; e < ix.tail; ++e) { float a = qs[ix.tail_off + e]; dot = __fadd_rn(dot, __fmul_rn(a, a)); }
-        } else {
-            dot = lane_raw_small<true, false>(qs, qs, ix.dims);
-        }
-        qn = __fsqrt_rn(dot);
-    } else if (ix.metric == HB_BQ_COSINE) {
-        qn = __fsqrt_rn((float)(int)(ix.n_words * 64u));
-    }
-    if (lane == 0) *qn_out = qn;
-    __syncwarp();
-}
 
 __global__ void __launch_bounds__(EX_WARPS * 32) exact_knn_kernel(const __grid_constant__ DevIndex ix, const float* __restrict__ q,
                                                                    uint64_t nq, uint32_t k, uint32_t* __restrict__ out_ids,
@@ -158,7 +109,17 @@ __global__ void __launch_bounds__(EX_WARPS * 32) exact_knn_kernel(const __grid_c
     }
 }
 
+hb_status launch_exact_knn_tc(const DevIndex& ix, const float* d_q, uint64_t nq, uint32_t k, uint32_t* d_ids, float* d_dist, void* stream, bool* done);
+
+// Exact k-NN: through the tensor-core shortlist (exact_tc.cu) where it applies, else the full CUDA-core scan.  Same output either way.
 hb_status launch_exact_knn(const DevIndex& ix, const float* d_q, uint64_t nq, uint32_t k, uint32_t* d_ids, float* d_dist, void* stream) {
+    bool done = false;
+    hb_status st = launch_exact_knn_tc(ix, d_q, nq, k, d_ids, d_dist, stream, &done);
+    if (st != HB_OK || done) return st;
+    return launch_exact_knn_scan(ix, d_q, nq, k, d_ids, d_dist, stream);
+}
+
+hb_status launch_exact_knn_scan(const DevIndex& ix, const float* d_q, uint64_t nq, uint32_t k, uint32_t* d_ids, float* d_dist, void* stream) {
     uint32_t qstride = (ix.row_stride + 15) & ~15u;
     size_t smem = (size_t)qstride * EX_TQ + 64 + (size_t)EX_WARPS * EX_TQ * k * 8 + EX_WARPS * EX_TQ * 4 + 16;
     if (smem > 200 * 1024) { set_error("exact_knn: k=%u / dims too large for shared memory (%zu bytes)", k, smem); return HB_EINVAL; }

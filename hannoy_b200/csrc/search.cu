@@ -37,6 +37,9 @@
 #ifndef HB_MIN_BLOCKS_BIN
 #define HB_MIN_BLOCKS_BIN 4  // binary codes: one lane per row, no ring -> shared memory is not the limit, registers are
 #endif
+#ifndef HB_EARLY_ROWS
+#define HB_EARLY_ROWS 1  // layer-0 deferred pops: request the rows of an expansion before merging the previous chunk into the heaps
+#endif
 #ifndef HB_MIN_BLOCKS_F32
 #define HB_MIN_BLOCKS_F32 3  // resident CTAs per SM the f32 kernel is compiled for (register budget)
 #endif
@@ -506,6 +509,7 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
     uint32_t csr_pos = 0, csr_end = 0;                       // rest of the CSR list being expanded
     float f_max = FLT_MAX;
     bool pend = false;
+    bool merge_deferred = false;   // the queue half of the pending chunk's merge runs after the next chunk's rows were requested (HB_EARLY_ROWS)
     ChunkUpdate u;
     u.mode = CH_EP; u.acc = u.pf = u.qskip = u.seq_done = false; u.bits = u.s = 0;
     for (;;) {
@@ -546,6 +550,20 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
                         if (can_cancel) ++c.polls;                 // the call that precedes this pop returned false
                         TR(c, TR_POP)
                         uint32_t a = (cs == spec_cs) ? spec_adj : __ldg(&nbrx[(size_t)cs * xstride + lane]);
+#if HB_EARLY_ROWS
+                        // Neither the visited filter nor the row gather of this expansion depends on the heaps, so the two merges of
+                        // the pending chunk are spread over the expansion's two memory round trips: the result-set merge runs while the
+                        // visited-set atomics are out, the queue merge (below, "merge_deferred") while the rows are being copied.
+                        if (xstride > FIXED_DEG && __shfl_sync(FULL, a, 31) != 0xffffffffu) { cont_cs = cs; csr_pos = FIXED_DEG; csr_end = xstride; }
+                        valid = a != 0xffffffffu;
+                        s = valid ? a : 0;
+                        old = vis_issue(c, s, valid);
+                        vis_sent = true;
+                        heaps_stage_res(c, u, ef);
+                        f_max = c.res_len ? key_dist(c.res[c.res_len - 1]) : FLT_MAX;  // what the reference reads at this pop
+                        merge_deferred = true;
+                        have = true;
+#else
                         heaps_stage_res(c, u, ef);                 // ... while the adjacency line is on its way
                         if (xstride > FIXED_DEG && __shfl_sync(FULL, a, 31) != 0xffffffffu) { cont_cs = cs; csr_pos = FIXED_DEG; csr_end = xstride; }
                         valid = a != 0xffffffffu;
@@ -564,6 +582,7 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
                         } else {
                             spec_cs = 0xffffffffu;
                         }
+#endif
                     }
                 }
             }
@@ -629,25 +648,47 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
         const unsigned lm = __ballot_sync(FULL, live);
         if (l01) PH_ADD(c, PH_VIS)
         TR(c, TR_VIS)
-        if (!lm) continue;
-        c.cur_dist += __popc(lm);
-        // ---- gather + distances ----
+        // ---- gather: start ----
         unsigned own = lm, helpers_used = 0;
         int per = 32;
-        if (KIND == KIND_F32_WARP && c.ts) {
-            team_update(c);
-            const int H = __popc(*c.team & 0xfu), n_live = __popc(lm);
-            if (H && n_live > ROW_GROUP) {
-                per = (((n_live + H) / (H + 1)) + ROW_GROUP - 1) & ~(ROW_GROUP - 1);
-                helpers_used = team_post(c, lm, s, per);
-                own = __ballot_sync(FULL, live && __popc(lm & ((1u << lane) - 1)) < per);
-            }
-        }
         RowsInFlight rf;
-        rows_begin<KIND>(c, own, s, rf);
-        TR(c, TR_POSTED)
+        if (lm) {
+            c.cur_dist += __popc(lm);
+            if (KIND == KIND_F32_WARP && c.ts) {
+                team_update(c);
+                const int H = __popc(*c.team & 0xfu), n_live = __popc(lm);
+                // worth it only when the rows do not fit this warp's ring in one go (short rows: one round trip either way)
+                if (H && n_live > max(ROW_GROUP, (int)c.ring.slots)) {
+                    per = (((n_live + H) / (H + 1)) + ROW_GROUP - 1) & ~(ROW_GROUP - 1);
+                    helpers_used = team_post(c, lm, s, per);
+                    own = __ballot_sync(FULL, live && __popc(lm & ((1u << lane) - 1)) < per);
+                }
+            }
+            rows_begin<KIND>(c, own, s, rf);
+            TR(c, TR_POSTED)
+        }
+        bool bail = false;
+        if (merge_deferred) {
+            // ---- the queue half of the PREVIOUS chunk's heap update, while this chunk's rows are in flight ----
+            if (l01) PH_ADD(c, PH_ROWS)
+            heaps_stage_queue(c, u, ef);
+            pend = false;
+            merge_deferred = false;
+            if (l01) PH_ADD(c, PH_HEAP)
+            TR(c, TR_HEAP)
+            if (!c.overflow && c.q_len > 0) {          // the adjacency line of the pop after this one
+                spec_cs = ~(uint32_t)c.que[c.q_len - 1];
+                spec_adj = __ldg(&nbrx[(size_t)spec_cs * xstride + lane]);
+            } else {
+                spec_cs = 0xffffffffu;
+            }
+            bail = c.overflow;                         // the merge ran out of room: drain the rows already posted, then leave
+        }
+        if (!lm) { if (bail) break; continue; }
+        // ---- gather: finish, distances ----
         float dist = rows_finish<KIND>(c, rf, s);
         if (KIND == KIND_F32_WARP && helpers_used) dist = team_collect(c, lm, helpers_used, per, dist);
+        if (bail) break;
         const uint32_t bits = __float_as_uint(dist);
         if (l01) PH_ADD(c, PH_ROWS)
         if (mode != CH_LINEAR && c.p.pass == 0 && !c.p.no_trim && __ballot_sync(FULL, live && (bits >> 31))) { c.overflow = true; break; }

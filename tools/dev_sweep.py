@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--trace", default="", help="HB_TRACE builds: save the event trace of one warp over one step (.npy)")
     ap.add_argument("--nq", type=int, default=0, help="override the batch size")
+    ap.add_argument("--device-build", action="store_true", help="build the graph on the device (seconds) instead of with the oracle builder")
     args = ap.parse_args()
     import torch
     import hannoy_b200 as hb
@@ -46,9 +47,20 @@ def main():
     q = bench.gen_vectors(w["gen"], w["nq"], w["dims"], w["seed"] + 1, dev)
     x_host, q_host = x.cpu().numpy(), q.cpu().numpy()
     del x
-    db = bench.build_or_load_graph(w, x_host, dev.type, threads, log)
-    rd = hb.Reader.from_arrays(w["metric"], w["dims"], db.ids(), db.rows(), db.headers(), db.layers(), db.entry_points,
-                               db.max_level, device=0)
+    if args.device_build:
+        from oracle.oracle import OracleDb
+        ids = np.arange(w["n"], dtype=np.uint32)
+        db = OracleDb(w["metric"], w["dims"])
+        db.add_items(ids, x_host)
+        rd = hb.Reader.build(w["metric"], w["dims"], ids, x_host, db.headers() if w["metric"] == "cosine" else None, M=16, M0=32, ef_construction=100, seed=42)
+        from oracle import oracle as O
+        for l, (off, nbr) in enumerate(rd.layers()):
+            O.lib().orc_db_set_csr(db.h, l, O._p(off), O._p(nbr), len(nbr))
+        db.set_entry_points(rd.entry_points(), rd.max_level())
+    else:
+        db = bench.build_or_load_graph(w, x_host, dev.type, threads, log)
+        rd = hb.Reader.from_arrays(w["metric"], w["dims"], db.ids(), db.rows(), db.headers(), db.layers(), db.entry_points,
+                                   db.max_level, device=0)
     k, nq = w["k"], w["nq"]
     ef_raw = max(args.ef, k)
     dq = q.contiguous()
