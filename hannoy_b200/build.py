@@ -22,7 +22,7 @@ FLAGS = [
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function",
 ]
 VARIANTS = {"": [], "phases": ["-DHB_PHASES"], "trace": ["-DHB_TRACE"], "rg2": ["-DHB_ROW_GROUP=2"],
-             "late": ["-DHB_EARLY_ROWS=0"], "bin5": ["-DHB_MIN_BLOCKS_BIN=5"], "bin6": ["-DHB_MIN_BLOCKS_BIN=6"], "bin8": ["-DHB_MIN_BLOCKS_BIN=8"]}
+             "late": ["-DHB_EARLY_ROWS=0"], "adjtop": ["-DHB_ADJ_PREFETCH_ALL=0"], "bin5": ["-DHB_MIN_BLOCKS_BIN=5"], "bin6": ["-DHB_MIN_BLOCKS_BIN=6"], "bin8": ["-DHB_MIN_BLOCKS_BIN=8"]}
 
 
 def out_path(variant=""):

@@ -25,6 +25,11 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// the same without release semantics: the arrival orders nothing this thread wrote (the waiter is the posting warp itself and
+// the data it waits for comes from the copy engine, ordered by complete_tx), so it need not wait for earlier stores
+__device__ __forceinline__ void mbar_expect_tx_relaxed(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.relaxed.cta.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     do {
@@ -61,7 +66,7 @@ struct RowRing {
 
     __device__ __forceinline__ void post(uint32_t slot, const void* row, uint32_t bytes) const {
         uint32_t bar = bars + slot * 8;
-        mbar_expect_tx(bar, bytes);
+        mbar_expect_tx_relaxed(bar, bytes);
         bulk_g2s(data + slot * stride, row, bytes, bar, policy);
     }
     __device__ __forceinline__ void wait(uint32_t slot) {

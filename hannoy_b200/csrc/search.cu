@@ -37,6 +37,9 @@
 #ifndef HB_MIN_BLOCKS_BIN
 #define HB_MIN_BLOCKS_BIN 4  // binary codes: one lane per row, no ring -> shared memory is not the limit, registers are
 #endif
+#ifndef HB_ADJ_PREFETCH_ALL
+#define HB_ADJ_PREFETCH_ALL 1
+#endif
 #ifndef HB_EARLY_ROWS
 #define HB_EARLY_ROWS 1  // layer-0 deferred pops: request the rows of an expansion before merging the previous chunk into the heaps
 #endif
@@ -131,19 +134,24 @@ enum ChunkMode { CH_EP, CH_NBR, CH_LINEAR };
 __device__ __forceinline__ uint32_t vis_issue(Ctx& c, uint32_t s, bool valid) {
     return valid ? atomicOr(&c.vis[s >> 5], 1u << (s & 31)) : 0xffffffffu;
 }
-__device__ __forceinline__ bool vis_finish(Ctx& c, uint32_t s, bool valid, uint32_t old) {
+// vis_finish leaves the slot's place in the touched list in `log_at` (UINT32_MAX: nothing to log); the store itself
+// (vis_log) is issued by the caller AFTER the row copies and helper jobs of the chunk were posted: an mbarrier arrive is a
+// release at CTA scope, and it would otherwise wait for this global store to be acknowledged.
+__device__ __forceinline__ bool vis_finish(Ctx& c, uint32_t s, bool valid, uint32_t old, uint32_t& log_at) {
     const bool fresh = valid && !((old >> (s & 31)) & 1u);
     unsigned m = __ballot_sync(FULL, fresh);
+    log_at = 0xffffffffu;
     if (m) {
         uint32_t r = __popc(m & ((1u << lane_id()) - 1));
         uint32_t at = c.touched_len + r;
-        if (fresh) {
-            if (at < c.p.touched_cap) c.touched[at] = s;
-        }
+        if (fresh && at < c.p.touched_cap) log_at = at;
         c.touched_len += __popc(m);
         if (c.touched_len > c.p.touched_cap) c.touched_over = true;
     }
     return fresh;
+}
+__device__ __forceinline__ void vis_log(Ctx& c, uint32_t s, uint32_t log_at) {
+    if (log_at != 0xffffffffu) c.touched[log_at] = s;
 }
 // path.clear() — reader.rs:743
 __device__ __forceinline__ void vis_clear(Ctx& c) {
@@ -639,12 +647,13 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
         }
         // ---- visited filter ----
         bool live = valid;
+        uint32_t log_at = 0xffffffffu;
         if (mode != CH_LINEAR) {
             if (!vis_sent) old = vis_issue(c, s, valid);
-            bool fresh = vis_finish(c, s, valid, old);           // `path.insert(..)`
+            bool fresh = vis_finish(c, s, valid, old, log_at);   // `path.insert(..)`
             if (mode == CH_NBR) live = fresh;                      // `if !path.insert(point) { continue }`; an ep's result is ignored
         }
-        if (c.overflow) break;                                     // (a deferred merge ran out of room)
+        if (c.overflow) { vis_log(c, s, log_at); break; }          // (a deferred merge ran out of room)
         const unsigned lm = __ballot_sync(FULL, live);
         if (l01) PH_ADD(c, PH_VIS)
         TR(c, TR_VIS)
@@ -659,7 +668,8 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
                 const int H = __popc(*c.team & 0xfu), n_live = __popc(lm);
                 // worth it only when the rows do not fit this warp's ring in one go (short rows: one round trip either way)
                 if (H && n_live > max(ROW_GROUP, (int)c.ring.slots)) {
-                    per = (((n_live + H) / (H + 1)) + ROW_GROUP - 1) & ~(ROW_GROUP - 1);
+                    const int share = H == 1 ? (n_live + 1) >> 1 : (H == 2 ? (n_live + 2) / 3 : (n_live + 3) >> 2);   // ceil(n_live / (H + 1))
+                    per = (share + ROW_GROUP - 1) & ~(ROW_GROUP - 1);
                     helpers_used = team_post(c, lm, s, per);
                     own = __ballot_sync(FULL, live && __popc(lm & ((1u << lane) - 1)) < per);
                 }
@@ -667,6 +677,7 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
             rows_begin<KIND>(c, own, s, rf);
             TR(c, TR_POSTED)
         }
+        vis_log(c, s, log_at);
         bool bail = false;
         if (merge_deferred) {
             // ---- the queue half of the PREVIOUS chunk's heap update, while this chunk's rows are in flight ----
@@ -704,7 +715,11 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
             acc = live && (fill || dist < f_max);
             // an accepted point that beats the queue's current best is expanded very soon: start pulling its adjacency line
 #ifndef HB_NO_ADJ_PREFETCH
+#if HB_ADJ_PREFETCH_ALL
+            if (nbrx && acc) prefetch_l2(nbrx + (size_t)s * xstride);   // 128 bytes per accepted point against a 3 KB row: every later pop finds its line in L2
+#else
             if (nbrx && acc && (c.q_len == 0 || bits <= (uint32_t)(c.que[c.q_len - 1] >> 32))) prefetch_l2(nbrx + (size_t)s * xstride);
+#endif
 #endif
         }
         u.mode = mode; u.acc = acc; u.pf = pf; u.qskip = false; u.bits = bits; u.s = s;
@@ -829,7 +844,7 @@ __device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64*
     c.cancelled = false; c.polls = 0;
     c.tr = false;
 #ifdef HB_TRACE
-    c.tr = slot_idx == 777 && p.pass == 0;
+    c.tr = slot_idx == (p.nq < 1000 ? 0 : 777) && p.pass == 0;
 #endif
     TR(c, TR_QSTART)
     c.n_dist_up = c.n_exp_up = c.n_deg_up = c.n_dist_l0 = c.n_exp_l0 = c.n_deg_l0 = 0;

@@ -2,8 +2,9 @@
 """BASELINE config 4 at FULL size on one B200 (GPU box): 10M x 1024 BinaryQuantizedCosine codes, graph built on the device
 (hb_index_build_graph — the CPU builder needs tens of minutes for this), 100k-query batches, top-100.  Reports build time,
 recall@100 against the exact k-NN kernel in the quantized metric, device-resident and end-to-end QPS, and size-independent
-properties of the results (sorted, unique, in range, self queries found).  Oracle parity at this size is not run (the oracle
-would need the graph through a 10M-callback export); it is established on the same code path at test sizes.
+properties of the results (sorted, unique, in range, self queries found), and ORACLE PARITY at full size: the device-built
+graph is handed to the CPU oracle as CSR (hb_index_layer_csr) and 256 queries are compared bit for bit (ids, distance bits,
+traversal counters) at the ef the recall rule picked.
 
   python tools/c4_full.py [--n-items 10000000] [--nq 100000] [--out file.json]
 """
@@ -14,14 +15,7 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 
-def quantize_bq(x):
-    """binary_quantized.rs:80-91: bit = sign bit clear, LSB-first in little-endian u64 words.  x: [m, dims] f32 on the GPU."""
-    import torch
-    m, dims = x.shape
-    assert dims % 64 == 0
-    bits = (~torch.signbit(x)).view(m, dims // 8, 8).to(torch.uint8)
-    w = torch.tensor([1, 2, 4, 8, 16, 32, 64, 128], dtype=torch.uint8, device=x.device)
-    return (bits * w).sum(dim=2, dtype=torch.uint8).cpu().numpy().view(np.uint64).reshape(m, dims // 64)
+quantize_bq = bench.quantize_bq
 
 
 def main():
@@ -68,6 +62,17 @@ def main():
     if ef_pick is None:
         ef_pick = max(sweep)
     log(f"recall@{k} sweep {sweep} -> ef_search={ef_pick}")
+    # oracle parity at full size: the CPU reader on the very same graph
+    t = time.time()
+    ids_all = np.arange(n, dtype=np.uint32)
+    db = bench.oracle_from_reader(rd, "binary quantized cosine", dims, codes, ids_all)
+    n_par = 256
+    want = db.search_by_vector(q_host[:n_par], k, ef=ef_pick, n_threads=len(os.sched_getaffinity(0)), counters=True)
+    got = rd.nns(k).ef_search(ef_pick).by_vectors_raw(q_host[:n_par], counters=True)
+    parity_ok = bool(np.array_equal(got[2], want[2]) and np.array_equal(got[0], want[0]) and np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32))
+                     and np.array_equal(got[3][:, :6], want[3][:, :6]))
+    log(f"oracle parity on {n_par} queries at ef={ef_pick}: {'bit-exact' if parity_ok else 'MISMATCH'} ({time.time() - t:.1f}s)")
+    del db
     # properties on the full batch
     ids, dd, lens = rd.nns(k).ef_search(ef_pick).by_vectors_raw(q_host)
     props = dict(all_full=bool((lens == k).all()), sorted=bool((np.diff(dd.view(np.uint32).astype(np.int64), axis=1) >= 0).all()),
@@ -111,7 +116,8 @@ def main():
                batch_queries=nq, k=k, M=16, M0=32, ef_construction=100, builder="device (hb_index_build_graph)", device_build_s=round(t_build, 1),
                device_build_stats=st, ef_search=ef_pick, recall_at_k=sweep[ef_pick], recall_sweep=sweep, ms_per_step=round(ms, 3),
                qps_device_resident=round(nq / ms * 1e3, 1), qps_e2e_host_buffers=round(nq / e2e_ms * 1e3, 1), algorithmic_gbs=round(alg / ms / 1e6, 1),
-               dist_evals_per_query=float(ctr[:, :2].sum() / nq), properties=props)
+               dist_evals_per_query=float(ctr[:, :2].sum() / nq), properties=props,
+               parity_vs_oracle=f"bit-exact (ids, distance bits, traversal counters; {n_par} queries at ef={ef_pick}, oracle on the exported device-built graph)" if parity_ok else "MISMATCH")
     print(json.dumps(res))
     if args.out:
         json.dump(res, open(args.out, "w"), indent=1)

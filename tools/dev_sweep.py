@@ -126,6 +126,15 @@ def main():
             n = L.hb_debug_trace(buf.ctypes.data, len(buf))
             np.save(args.trace, buf[:n])
             r["trace_events"] = int(n)
+            # mean cycles between consecutive events, by (previous event -> event) pair
+            names = {1: "qstart", 2: "pop", 3: "adj", 4: "vis", 5: "posted", 6: "rowwait", 7: "group", 8: "heap", 9: "qend", 10: "l0"}
+            ev = (buf[:n] & 0xff).astype(int)
+            ts = (buf[:n] >> 8).astype(np.int64)
+            pairs = {}
+            for i in range(1, n):
+                key = f"{names.get(ev[i - 1], ev[i - 1])}->{names.get(ev[i], ev[i])}"
+                pairs.setdefault(key, []).append(int(ts[i] - ts[i - 1]))
+            r["trace_pairs"] = {k: {"n": len(v), "mean": round(float(np.mean(v))), "p50": int(np.median(v))} for k, v in sorted(pairs.items(), key=lambda kv: -sum(kv[1]))[:16]}
         results.append(r)
         print(json.dumps(r), flush=True)
     if args.out:
