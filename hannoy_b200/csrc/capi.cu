@@ -425,6 +425,7 @@ hb_status hb_index_finalize(hb_index* ix, int device) {
     }
     if ((st = upload(ix, ix->eps.data(), ix->eps.size(), &d.eps)) != HB_OK) return st;
     d.n_ep = (uint32_t)ix->eps.size();
+    ix->have_rows_tmap = n && d.kind == KIND_F32_WARP && d.row_stride <= 1024 && d.row_stride % 128 == 0 /* tensor copies land on 128-byte boundaries */ && make_row_gather_map(ix->rows_tmap, d.rows, n, d.row_stride / 4, d.row_stride);
     ix->finalized = true;
     return HB_OK;
 }
@@ -460,6 +461,7 @@ static hb_status replicate_one(const hb_index* ix, int device, hb_index** out) {
     d.rows = (const uint8_t*)rebase(ix->dev.rows); d.hdr = (const float*)rebase(ix->dev.hdr); d.ids = (const uint32_t*)rebase(ix->dev.ids);
     d.eps = (const uint32_t*)rebase(ix->dev.eps); d.nbr0x = (const uint32_t*)rebase(ix->dev.nbr0x);
     for (uint32_t l = 0; l < d.n_layers; ++l) { d.off[l] = (const uint32_t*)rebase(ix->dev.off[l]); d.nbr[l] = (const uint32_t*)rebase(ix->dev.nbr[l]); }
+    r->have_rows_tmap = ix->have_rows_tmap && make_row_gather_map(r->rows_tmap, d.rows, d.n, d.row_stride / 4, d.row_stride);
     if (cudaDeviceSynchronize() != cudaSuccess) { set_error("replication to device %d failed: %s", device, cudaGetErrorString(cudaGetLastError())); return fail(HB_ECUDA); }
     *out = r;
     return HB_OK;
@@ -688,11 +690,13 @@ static hb_status run_search(const hb_index* ix, Workspace* w, SearchParams base,
         slots = std::max<uint32_t>(ROW_GROUP, std::min<uint32_t>(slots, 32));
         base.ring_slots = slots;
         base.ring_stride = d.row_stride;
+        if (ix->have_rows_tmap && ROW_GROUP == 4 && tunable("gather4", 1)) { base.gather4 = 1; std::memcpy(base.rows_tmap, ix->rows_tmap, 128); }
         SearchParams probe = base;
         probe.pass = 1;
         if (search_smem_per_warp(probe) * SEARCH_WARPS_PER_BLOCK > (size_t)SEARCH_MAX_SMEM) {
             base.ring_slots = 0;  // rows too long to stage: direct global-memory gather
             base.ring_stride = 0;
+            base.gather4 = 0;
         }
     }
     SearchParams fast = base, slow = base;

@@ -104,6 +104,10 @@ struct SearchParams {
     int no_trim = 0;                   // graph builder, metrics with negative distances: shared-memory heaps without dead-entry trimming,
                                        // no deferred pops (the literal reference loop); a negative distance does not end the walk
     int defer = 1;                     // layer 0, pass 0: overlap a chunk's heap update with the next pop's adjacency / visited traffic
+    // f32 rows of at most 1 KB: the ring is fed four rows per instruction through a 2-D tensor map of the row array
+    // (TMA tile::gather4; box = one row).  The 128-byte CUtensorMap is carried by value (it must live in param space).
+    alignas(64) unsigned char rows_tmap[128] = {};
+    int gather4 = 0;
     int team = 1;                      // f32 ring kernel: warps of a CTA that ran out of queries gather rows for the ones still walking
     uint32_t n_static = 0;             // queries handed out by position (warp w of CTA b starts with query w * gridDim + b), the rest by counter
 };
@@ -195,6 +199,8 @@ struct hb_index {
     std::vector<hb_index*> replicas;
     const hb_index* host() const { return primary ? primary : this; }
     hb::DevIndex dev;
+    alignas(64) unsigned char rows_tmap[128] = {};   // CUtensorMap over dev.rows (one row per box) for the gather4 ring, if have_rows_tmap
+    bool have_rows_tmap = false;
     std::vector<void*> dev_allocs;
     std::vector<size_t> dev_alloc_bytes;  // parallel to dev_allocs (replication copies buffer by buffer)
     std::mutex ws_mu;
@@ -223,6 +229,8 @@ hb_status snapshot_load(hb_index* ix, const uint8_t* data, size_t size);
 typedef hb_status (*lmdb_visit_fn)(void* user, const uint8_t* key, size_t klen, const uint8_t* val, size_t vlen, unsigned node_flags);
 hb_status lmdb_scan(const char* path, const char* db_name, const uint8_t* prefix, size_t prefix_len, lmdb_visit_fn fn, void* user,
                     uint64_t* txnid_out);
+// exact_tc.cu: a CUtensorMap over a row-major f32 array whose box is one whole row of `kfloats` (<= 256) floats, unswizzled
+bool make_row_gather_map(void* out128, const void* base, uint64_t rows, uint64_t kfloats, uint64_t row_bytes);
 // device row layout
 uint32_t device_row_stride(int kind, uint32_t dims);
 void layout_row(int kind, uint32_t dims, const uint8_t* natural, uint8_t* out);

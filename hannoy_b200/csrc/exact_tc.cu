@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -361,6 +362,22 @@ struct DevFrees {
 };
 
 }  // namespace
+
+bool make_row_gather_map(void* out128, const void* base, uint64_t rows, uint64_t kfloats, uint64_t row_bytes) {
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+    encode_tiled_fn enc = tensor_map_encoder();
+    if (!enc || kfloats == 0 || kfloats > 256 || (row_bytes & 15u)) return false;
+    alignas(64) CUtensorMap m;
+    cuuint64_t gdim[2] = {kfloats, rows};
+    cuuint64_t gstr[1] = {row_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)kfloats, 1};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    memcpy(out128, &m, 128);
+    return true;
+}
 
 // tf32 error model behind the candidate test: both operands lose at most their 13 low mantissa bits (relative 2^-10 each, 2^-9
 // for the product, to first order), the products are exact, the fp32 accumulation of K terms adds at most K * 2^-23 relative to

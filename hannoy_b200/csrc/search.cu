@@ -189,6 +189,7 @@ struct RowsInFlight {
     bool has;
     const uint8_t* grow;  // this lane's row in global memory
     float in;             // this lane's item header (norm)
+    uint32_t g1, g2, g3;  // gather4 ring: the slots of the three live rows after this lane's (UINT32_MAX past the last), for lanes of rank % 4 == 0
 };
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -203,11 +204,19 @@ __device__ __forceinline__ void rows_begin(Ctx& c, unsigned mask, uint32_t s, Ro
     rf.rank = __popc(mask & ((1u << lane) - 1));
     rf.grow = ix.rows + (size_t)s * ix.row_stride;
     rf.in = 0.0f;
+    if (KIND == KIND_F32_WARP && c.p.gather4) {
+        // four rows per copy instruction: the lane that owns live row 4g collects the slots of rows 4g+1..4g+3
+        const unsigned l1 = __fns(mask, lane, 2), l2 = __fns(mask, lane, 3), l3 = __fns(mask, lane, 4);
+        const uint32_t s1 = __shfl_sync(FULL, s, l1 & 31), s2 = __shfl_sync(FULL, s, l2 & 31), s3 = __shfl_sync(FULL, s, l3 & 31);
+        rf.g1 = l1 < 32 ? s1 : ix.n; rf.g2 = l2 < 32 ? s2 : ix.n; rf.g3 = l3 < 32 ? s3 : ix.n;   // a row index past the end reads as zeros
+    }
     if (!rf.has) return;
     if (KIND == KIND_F32_WARP) {
         // Row r (in ascending-lane order) lands in ring slot r % S: the first S copies are posted at once by the
         // lanes that own them.
-        if (rf.rank < (int)c.ring.slots) c.ring.post(rf.rank, rf.grow, ix.row_stride);
+        if (c.p.gather4) {
+            if ((rf.rank & 3) == 0 && rf.rank < (int)c.ring.slots) c.ring.post_gather4(rf.rank, c.p.rows_tmap, s, rf.g1, rf.g2, rf.g3);
+        } else if (rf.rank < (int)c.ring.slots) c.ring.post(rf.rank, rf.grow, ix.row_stride);
         if (ix.metric == HB_COSINE) rf.in = __ldg(&ix.hdr[s]);
     } else if (KIND == KIND_F32_DIRECT) {
         if (ix.metric == HB_COSINE) rf.in = __ldg(&ix.hdr[s]);
@@ -259,14 +268,16 @@ __device__ __forceinline__ float rows_finish(Ctx& c, const RowsInFlight& rf, uin
             const uint8_t* rowp[ROW_GROUP];
 #pragma unroll
             for (int r = 0; r < ROW_GROUP; ++r) {
-                if (r < g) { c.ring.wait(slot0 + r); TR(c, TR_ROWWAIT) }
+                if (r < g && (r == 0 || !c.p.gather4)) { c.ring.wait(slot0 + r); TR(c, TR_ROWWAIT) }   // a gathered group completes on its first slot's barrier
                 rowp[r] = c.ring.ptr + (size_t)(slot0 + (r < g ? r : 0)) * c.ring.stride;
             }
             // row r's sum comes back on lane group_owner(r); the lane that owns the row picks it up
             float red = (ix.metric == HB_COSINE) ? warp_rows_group<ROW_GROUP, true, true>(ix, c.qs, rowp) : warp_rows_group<ROW_GROUP, false, true>(ix, c.qs, rowp);
             __syncwarp();  // every lane has read the group's slots: they may be overwritten
             const int nxt = rf.rank - r0 - S;
-            if (rf.has && nxt >= 0 && nxt < g) c.ring.post(slot0 + nxt, rf.grow, ix.row_stride);
+            if (c.p.gather4) {
+                if (rf.has && nxt == 0) c.ring.post_gather4(slot0, c.p.rows_tmap, s, rf.g1, rf.g2, rf.g3);
+            } else if (rf.has && nxt >= 0 && nxt < g) c.ring.post(slot0 + nxt, rf.grow, ix.row_stride);
             const int mr = rf.rank - r0;
             const float got = __shfl_sync(FULL, red, group_owner<ROW_GROUP>(mr >= 0 && mr < ROW_GROUP ? mr : 0));
             if (rf.has && mr >= 0 && mr < g) myraw = got;
