@@ -89,7 +89,7 @@ int hb_metric_from_name(const char* name) {
 }
 const char* hb_last_error(void) { return last_error(); }
 uint64_t hb_launch_count(void) { return g_launches; }
-void hb_debug_phases(uint64_t* out8) { if (out8) read_phases((unsigned long long*)out8); }
+void hb_debug_phases(uint64_t* out16) { if (out16) read_phases((unsigned long long*)out16); }
 uint32_t hb_debug_trace(uint64_t* out, uint32_t cap) { return out ? read_trace((unsigned long long*)out, cap) : 0; }
 hb_status hb_tune(const char* key, int value) {
     if (!key) return HB_EINVAL;

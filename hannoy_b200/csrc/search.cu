@@ -77,7 +77,7 @@ __device__ unsigned int g_trace_n;
 #define TR(c, ev) {}
 #endif
 enum { TR_QSTART = 1, TR_POP = 2, TR_ADJ = 3, TR_VIS = 4, TR_POSTED = 5, TR_ROWWAIT = 6, TR_GROUP = 7, TR_HEAP = 8, TR_QEND = 9, TR_L0 = 10 };
-enum { PH_STAGE = 0, PH_UPPER = 1, PH_ADJ = 2, PH_VIS = 3, PH_ROWS = 4, PH_HEAP = 5, PH_TAIL = 6, PH_TOTAL = 7, PH_N = 8 };
+enum { PH_STAGE = 0, PH_UPPER = 1, PH_ADJ = 2, PH_VIS = 3, PH_ROWS = 4, PH_HEAP = 5, PH_TAIL = 6, PH_TOTAL = 7, PH_POST = 8, PH_COLLECT = 9, PH_ACCEPT = 10, PH_DECIDE = 11, PH_N = 12 };
 
 struct Ctx {
     const SearchParams& p;
@@ -206,9 +206,14 @@ __device__ __forceinline__ void rows_begin(Ctx& c, unsigned mask, uint32_t s, Ro
     rf.in = 0.0f;
     if (KIND == KIND_F32_WARP && c.p.gather4) {
         // four rows per copy instruction: the lane that owns live row 4g collects the slots of rows 4g+1..4g+3
-        const unsigned l1 = __fns(mask, lane, 2), l2 = __fns(mask, lane, 3), l3 = __fns(mask, lane, 4);
+        // (next set bit above a lane: clear the bits up to it, take the lowest — __fns would be a loop)
+        const unsigned m1 = mask & ~((2u << lane) - 1u);
+        const int l1 = __ffs(m1) - 1;
+        const unsigned m2 = m1 & (m1 - 1u);
+        const int l2 = __ffs(m2) - 1;
+        const int l3 = __ffs(m2 & (m2 - 1u)) - 1;
         const uint32_t s1 = __shfl_sync(FULL, s, l1 & 31), s2 = __shfl_sync(FULL, s, l2 & 31), s3 = __shfl_sync(FULL, s, l3 & 31);
-        rf.g1 = l1 < 32 ? s1 : ix.n; rf.g2 = l2 < 32 ? s2 : ix.n; rf.g3 = l3 < 32 ? s3 : ix.n;   // a row index past the end reads as zeros
+        rf.g1 = l1 >= 0 ? s1 : ix.n; rf.g2 = l2 >= 0 ? s2 : ix.n; rf.g3 = l3 >= 0 ? s3 : ix.n;   // a row index past the end reads as zeros
     }
     if (!rf.has) return;
     if (KIND == KIND_F32_WARP) {
@@ -314,7 +319,10 @@ struct TeamShared {
     uint32_t owner[SEARCH_WARPS_PER_BLOCK];               // TEAM_BUSY | TEAM_FREE | warp index of the leader holding it
     uint32_t done_parity[SEARCH_WARPS_PER_BLOCK];         // parity the next wait on done_bar[h] must observe (handed from holder to holder)
     uint32_t n_idle;
-    struct Job { const float* qs; float qn; uint32_t n; uint32_t slot[32]; float dist[32]; } job[SEARCH_WARPS_PER_BLOCK];
+    // a job, written by the leader for helper h: the leader's staged query, the range [lo, lo + n) of live rows (by rank) to do
+    struct Job { const float* qs; float qn; uint32_t lo, n, leader; } job[SEARCH_WARPS_PER_BLOCK];
+    uint32_t slot[SEARCH_WARPS_PER_BLOCK][32];   // per LEADER warp: the slots of the chunk's live rows, by rank
+    float dist[SEARCH_WARPS_PER_BLOCK][32];      // per LEADER warp: their distances, by rank (each helper fills its range)
 };
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {   // .release.cta
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -370,44 +378,53 @@ __device__ __forceinline__ void team_release(TeamShared& ts, uint32_t& team) {
     __syncwarp();
 }
 
+// the j-th (j = 0..2) set bit of a 4-bit helper mask
+__device__ __forceinline__ int team_nth(unsigned hm, int j) {
+    const unsigned m1 = hm & (hm - 1u), m2 = m1 & (m1 - 1u);
+    return __ffs(j == 0 ? hm : (j == 1 ? m1 : m2)) - 1;
+}
+
 // leader: share the live rows of one chunk out over the attached helpers.  Rows are split in order of rank, in whole
-// reduction groups: the leader keeps [0, per), the j-th helper takes [j * per, (j + 1) * per).  team_post hands the
-// helpers their slots and returns the mask of helpers used; team_collect waits for them and picks the distances up.
+// reduction groups: the leader keeps [0, per), the j-th helper takes [j * per, (j + 1) * per).  Everything is done once for
+// all helpers — a lone warp pays every instruction's latency in full, so the hand-off is a handful of instructions: all live
+// lanes store their slot by rank, lane j describes helper j's range and arrives on its job barrier.  team_post returns the mask
+// of LANES that manage a helper in use; team_collect has those lanes wait for their helper, then every lane picks its distance.
 __device__ __forceinline__ unsigned team_post(Ctx& c, unsigned lm, uint32_t s, int per) {
     TeamShared& ts = *c.ts;
     const int lane = lane_id();
+    const uint32_t me = threadIdx.x >> 5;
     const int n_live = __popc(lm);
-    const bool has = (lm >> lane) & 1;
     const int rank = __popc(lm & ((1u << lane) - 1));
-    unsigned used = 0;
-    int j = 1;
-    for (unsigned m = *c.team & 0xfu; m && j * per < n_live; m &= m - 1, ++j) {
-        const int h = __ffs(m) - 1, lo = j * per, hi = min(n_live, lo + per);
+    if ((lm >> lane) & 1) ts.slot[me][rank] = s;
+    const unsigned hm = *c.team & 0xfu;
+    const int lo = (lane + 1) * per;
+    const bool mine = lane < __popc(hm) && lo < n_live;      // lane j manages the j-th attached helper
+    const int h = team_nth(hm, lane);
+    if (mine) {
         TeamShared::Job& jb = ts.job[h];
-        if (has && rank >= lo && rank < hi) jb.slot[rank - lo] = s;
-        if (lane == 0) { jb.n = (uint32_t)(hi - lo); jb.qs = c.qs; jb.qn = c.qn; }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_addr(&ts.job_bar[h]));
-        used |= 1u << h;
+        jb.qs = c.qs; jb.qn = c.qn; jb.lo = (uint32_t)lo; jb.n = (uint32_t)(min(n_live, lo + per) - lo); jb.leader = me;
     }
-    return used;
+    __syncwarp();
+    if (mine) mbar_arrive(smem_addr(&ts.job_bar[h]));
+    return __ballot_sync(FULL, mine);
 }
 __device__ __forceinline__ float team_collect(Ctx& c, unsigned lm, unsigned used, int per, float d) {
     TeamShared& ts = *c.ts;
     const int lane = lane_id();
-    const int n_live = __popc(lm);
-    const bool has = (lm >> lane) & 1;
-    const int rank = __popc(lm & ((1u << lane) - 1));
-    int j = 1;
-    for (unsigned m = used; m; m &= m - 1, ++j) {
-        const int h = __ffs(m) - 1, lo = j * per, hi = min(n_live, lo + per);
+    const uint32_t me = threadIdx.x >> 5;
+    const unsigned hm = *c.team & 0xfu;
+    unsigned flip = 0;
+    if ((used >> lane) & 1) {
+        const int h = team_nth(hm, lane);
         const uint32_t bar = smem_addr(&ts.done_bar[h]);
         while (!mbar_try_wait(bar, (*c.team >> (4 + h)) & 1u)) {}
-        *c.team ^= 1u << (4 + h);
-        if (has && rank >= lo && rank < hi) d = ts.job[h].dist[rank - lo];
+        flip = 1u << (4 + h);
     }
-    __syncwarp();
-    return d;
+    __syncwarp();                               // the waiting lanes' acquire is ordered before every lane's read below
+    *c.team ^= __reduce_or_sync(FULL, flip);
+    const int rank = __popc(lm & ((1u << lane) - 1));
+    if (((lm >> lane) & 1) && rank >= per) d = ts.dist[me][rank];
+    return d;   // (the next hand-off's __syncwarp, before its arrive, keeps a helper's next write behind these reads)
 }
 
 // helper: serve jobs until every warp of the CTA is idle
@@ -421,16 +438,16 @@ __device__ __noinline__ void team_help(const SearchParams& p, TeamShared& ts, Ro
         while (!mbar_try_wait(jbar, par))
             if (ld_volatile_shared(&ts.n_idle) >= (uint32_t)SEARCH_WARPS_PER_BLOCK) return;
         par ^= 1u;
-        TeamShared::Job& jb = ts.job[me];
+        const TeamShared::Job& jb = ts.job[me];
         Ctx c(p, ring);
         c.qs = jb.qs; c.qn = jb.qn; c.tr = false;
-        const uint32_t n = jb.n;
+        const uint32_t n = jb.n, lo = jb.lo, leader = jb.leader;
         const bool has = (uint32_t)lane < n;
-        const uint32_t s = has ? jb.slot[lane] : 0u;
+        const uint32_t s = has ? ts.slot[leader][lo + lane] : 0u;
         RowsInFlight rf;
         rows_begin<KIND>(c, __ballot_sync(FULL, has), s, rf);
         const float d = rows_finish<KIND>(c, rf, s);
-        if (has) jb.dist[lane] = d;
+        if (has) ts.dist[leader][lo + lane] = d;
         __syncwarp();
         if (lane == 0) mbar_arrive(dbar);
     }
@@ -568,6 +585,7 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
                         c.cur_exp += 1;
                         if (can_cancel) ++c.polls;                 // the call that precedes this pop returned false
                         TR(c, TR_POP)
+                        if (l01) PH_ADD(c, PH_DECIDE)
                         uint32_t a = (cs == spec_cs) ? spec_adj : __ldg(&nbrx[(size_t)cs * xstride + lane]);
 #if HB_EARLY_ROWS
                         // Neither the visited filter nor the row gather of this expansion depends on the heaps, so the two merges of
@@ -685,6 +703,7 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
                     own = __ballot_sync(FULL, live && __popc(lm & ((1u << lane) - 1)) < per);
                 }
             }
+            if (l01) PH_ADD(c, PH_POST)
             rows_begin<KIND>(c, own, s, rf);
             TR(c, TR_POSTED)
         }
@@ -709,10 +728,11 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
         if (!lm) { if (bail) break; continue; }
         // ---- gather: finish, distances ----
         float dist = rows_finish<KIND>(c, rf, s);
+        if (l01) PH_ADD(c, PH_ROWS)
         if (KIND == KIND_F32_WARP && helpers_used) dist = team_collect(c, lm, helpers_used, per, dist);
         if (bail) break;
         const uint32_t bits = __float_as_uint(dist);
-        if (l01) PH_ADD(c, PH_ROWS)
+        if (l01) PH_ADD(c, PH_COLLECT)
         if (mode != CH_LINEAR && c.p.pass == 0 && !c.p.no_trim && __ballot_sync(FULL, live && (bits >> 31))) { c.overflow = true; break; }
         // ---- which points are accepted, and which of those may enter the result set (reader.rs:322,353,355-359) ----
         const bool pf = live && passes_filter(c, s, filt);
@@ -735,6 +755,7 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
         }
         u.mode = mode; u.acc = acc; u.pf = pf; u.qskip = false; u.bits = bits; u.s = s;
         pend = true;
+        if (l01) PH_ADD(c, PH_ACCEPT)
     }
     if (level) { c.n_dist_up += c.cur_dist; c.n_exp_up += c.cur_exp; c.n_deg_up += c.cur_deg; }
     else { c.n_dist_l0 += c.cur_dist; c.n_exp_l0 += c.cur_exp; c.n_deg_l0 += c.cur_deg; }

@@ -15,9 +15,10 @@ extern "C" {
 hb_status hb_tune(const char* key, int value);
 
 /* Development aid: cycles per phase of the search kernel summed over all queries since the last call
- * (stage, upper layers, adjacency wait, visited filter, row gather+distance, heap update, tail, total).
+ * (stage, upper layers, adjacency wait, visited filter, row gather+distance, heap update, tail, total, helper jobs posted,
+ * helper results collected, accept step, pop decision; 16 slots).
  * All zero unless the library was built with -DHB_PHASES. */
-void hb_debug_phases(uint64_t* out8);
+void hb_debug_phases(uint64_t* out16);
 /* Development aid: event trace (clock64 << 8 | event id) of one query warp since the last call; returns the
  * number of records copied.  Always 0 unless the library was built with -DHB_TRACE. */
 uint32_t hb_debug_trace(uint64_t* out, uint32_t cap);

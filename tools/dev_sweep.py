@@ -100,7 +100,7 @@ def main():
         for _ in range(3):
             step()
         torch.cuda.synchronize()
-        ph0 = np.zeros(8, np.uint64)
+        ph0 = np.zeros(16, np.uint64)
         L.hb_debug_phases(ph0.ctypes.data)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -109,13 +109,13 @@ def main():
         e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
-        ph = np.zeros(8, np.uint64)
+        ph = np.zeros(16, np.uint64)
         L.hb_debug_phases(ph.ctypes.data)
         r = dict(tune=dict(zip(keys, combo)), ms=round(ms, 3), qps=round(nq / ms * 1e3), gbs=round(alg / ms / 1e6, 1), parity=ok, counters=ok_ctr,
                  slow=int((ctr[:, 6] & 4).astype(bool).sum()), evals_per_q=float(ctr[:, :2].sum() / nq), exp_per_q=float(ctr[:, 2:4].sum() / nq))
         if ph.sum():
             tot = float(ph[7]) or 1.0
-            names = ["stage", "upper", "adj", "vis", "rows", "heap", "tail", "total"]
+            names = ["stage", "upper", "adj", "vis", "rows", "heap", "tail", "total", "post", "collect", "accept", "decide"]
             r["phase_frac"] = {n: round(float(p) / tot, 3) for n, p in zip(names, ph)}
             r["cycles_per_query"] = round(tot / (nq * args.steps))
         if args.trace:
