@@ -22,7 +22,14 @@ FLAGS = [
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function",
 ]
 VARIANTS = {"": [], "phases": ["-DHB_PHASES"], "trace": ["-DHB_TRACE"], "rg2": ["-DHB_ROW_GROUP=2"],
-             "late": ["-DHB_EARLY_ROWS=0"], "adjtop": ["-DHB_ADJ_PREFETCH_ALL=0"], "bin5": ["-DHB_MIN_BLOCKS_BIN=5"], "bin6": ["-DHB_MIN_BLOCKS_BIN=6"], "bin8": ["-DHB_MIN_BLOCKS_BIN=8"]}
+            "late": ["-DHB_EARLY_ROWS=0"], "adjtop": ["-DHB_ADJ_PREFETCH_ALL=0"]}
+for _b in (4, 5, 6, 7, 8):   # dev: occupancy the binary / f32 ring kernels are compiled for, heap-merge block size
+    VARIANTS[f"bin{_b}"] = [f"-DHB_MIN_BLOCKS_BIN={_b}"]
+    VARIANTS[f"g2bin{_b}"] = [f"-DHB_MIN_BLOCKS_BIN={_b}", "-DHB_MERGE_BLOCK=2"]
+    VARIANTS[f"f32b{_b}"] = [f"-DHB_MIN_BLOCKS_F32={_b}"]
+    VARIANTS[f"g2f32b{_b}"] = [f"-DHB_MIN_BLOCKS_F32={_b}", "-DHB_MERGE_BLOCK=2"]
+for _g in (1, 2, 3, 8):
+    VARIANTS[f"g{_g}"] = [f"-DHB_MERGE_BLOCK={_g}"]
 
 
 def out_path(variant=""):

@@ -400,6 +400,15 @@ hb_status hb_index_finalize(hb_index* ix, int device) {
     d.n_layers = (uint32_t)ix->layers.size();
     if (d.n_layers > (uint32_t)MAX_LEVELS) { set_error("too many layers"); return HB_EINVAL; }
     if ((st = upload(ix, ix->host_hdr.data(), n, &d.hdr)) != HB_OK) return st;
+    d.hdr_uniform = 0;
+    if (n && d.kind == KIND_BIN) {   // one scattered 4-byte load (a 32-byte DRAM sector) per distance saved when the headers are all alike
+        uint32_t h0, hi;
+        std::memcpy(&h0, &ix->host_hdr[0], 4);
+        bool same = true;
+        for (size_t i = 1; i < n && same; ++i) { std::memcpy(&hi, &ix->host_hdr[i], 4); same = hi == h0; }
+        d.hdr_uniform = same ? 1 : 0;
+        d.hdr_value = ix->host_hdr[0];
+    }
     if ((st = upload(ix, ix->ids.data(), n, &d.ids)) != HB_OK) return st;
     for (uint32_t l = 0; l < d.n_layers; ++l) {
         HostLayer& hl = ix->layers[l];
@@ -685,11 +694,15 @@ static hb_status run_search(const hb_index* ix, Workspace* w, SearchParams base,
         // rows in flight per warp: as many as fit the ring budget, in whole reduction groups (512-byte rows: the
         // whole neighbour list of an expansion in one shot).  "ring_min_row" routes shorter rows to the plain-load
         // gather (search.cu KIND_F32_DIRECT) instead; measured slower on C2 (1.57M vs 1.84M QPS), so off by default.
-        uint32_t budget = (uint32_t)std::max(0, tunable("ring_bytes", 12288));
+        // Short rows (a reduction group of four fits 8 KB) take an 8 KB ring: four CTAs per SM then fit and the kernel's
+        // instantiation compiled for four is used (C2, 512-byte rows: 12 KB x 3 CTAs 1.65 M QPS, 8 KB x 4 CTAs 1.81 M).
+        const bool short_rows = d.row_stride * ROW_GROUP <= 8192;
+        uint32_t budget = (uint32_t)std::max(0, tunable("ring_bytes", short_rows ? 8192 : 12288));
         uint32_t slots = budget / d.row_stride / ROW_GROUP * ROW_GROUP;
         slots = std::max<uint32_t>(ROW_GROUP, std::min<uint32_t>(slots, 32));
         base.ring_slots = slots;
         base.ring_stride = d.row_stride;
+        base.ring_short = tunable("ring_short", short_rows ? 1 : 0);
         if (ix->have_rows_tmap && ROW_GROUP == 4 && tunable("gather4", 1)) { base.gather4 = 1; std::memcpy(base.rows_tmap, ix->rows_tmap, 128); }
         SearchParams probe = base;
         probe.pass = 1;
@@ -697,6 +710,7 @@ static hb_status run_search(const hb_index* ix, Workspace* w, SearchParams base,
             base.ring_slots = 0;  // rows too long to stage: direct global-memory gather
             base.ring_stride = 0;
             base.gather4 = 0;
+            base.ring_short = 0;
         }
     }
     SearchParams fast = base, slow = base;

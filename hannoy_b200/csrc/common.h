@@ -42,6 +42,8 @@ struct DevIndex {
     uint32_t n_words = 0;     // KIND_BIN: u64 words per row = ceil(dims/64)
     const uint8_t* rows = nullptr;
     const float* hdr = nullptr;      // per-slot norm (Cosine, BQ-Cosine) or nullptr
+    int hdr_uniform = 0;             // every item carries the same header (always so for BQ-Cosine: sqrt(bq_dot(v, v)) = sqrt(padded
+    float hdr_value = 0.0f;          // length), binary_quantized_cosine.rs:36-38) -> the walk uses hdr_value instead of loading hdr[s]
     const uint32_t* ids = nullptr;   // slot -> ItemId
     uint32_t n_layers = 0;
     uint32_t max_level = 0;
@@ -89,6 +91,7 @@ struct SearchParams {
     uint32_t q_smem_bytes = 0;         // per-warp query staging bytes
     uint32_t ring_slots = 0;           // KIND_F32_WARP: rows in flight per warp (multiple of ROW_GROUP), ring.cuh
     uint32_t ring_stride = 0;          // bytes between ring slots
+    int ring_short = 0;                // short rows: the instantiation of the ring kernel compiled for one more resident CTA per SM
     // id-sharded search with the all-gather fused into the epilogue: every query's padded top-k is stored straight into
     // each peer's gather buffer [shard][nq][count] over NVLink (peer_ids[p] / peer_dist[p] are peer-mapped device pointers)
     uint32_t* peer_ids[HB_MAX_SHARDS] = {};

@@ -35,8 +35,8 @@
 #define HB_MIN_BLOCKS_DIRECT 4
 #endif
 #ifndef HB_MIN_BLOCKS_BIN
-#define HB_MIN_BLOCKS_BIN 4  // binary codes: one lane per row, no ring -> shared memory is not the limit, registers are
-#endif
+#define HB_MIN_BLOCKS_BIN 6  // binary codes: one lane per row, no ring -> shared memory is not the limit, registers are (80 per thread;
+#endif                       // the walk is a dependent chain per warp, so more resident warps beat a few spilled cold values: 4 -> 6 CTAs/SM = +15 % on C4s)
 #ifndef HB_ADJ_PREFETCH_ALL
 #define HB_ADJ_PREFETCH_ALL 1
 #endif
@@ -44,7 +44,10 @@
 #define HB_EARLY_ROWS 1  // layer-0 deferred pops: request the rows of an expansion before merging the previous chunk into the heaps
 #endif
 #ifndef HB_MIN_BLOCKS_F32
-#define HB_MIN_BLOCKS_F32 3  // resident CTAs per SM the f32 kernel is compiled for (register budget)
+#define HB_MIN_BLOCKS_F32 3  // resident CTAs per SM the f32 ring kernel is compiled for (register budget): long rows, shared memory allows no more
+#endif
+#ifndef HB_MIN_BLOCKS_F32_SHORT
+#define HB_MIN_BLOCKS_F32_SHORT 4  // ... and its second instantiation for rows short enough that four CTAs' rings fit one SM (C2: +10 %)
 #endif
 
 namespace hb {
@@ -227,7 +230,7 @@ __device__ __forceinline__ void rows_begin(Ctx& c, unsigned mask, uint32_t s, Ro
         if (ix.metric == HB_COSINE) rf.in = __ldg(&ix.hdr[s]);
     } else {
         for (uint32_t o = 0; o < ix.row_stride; o += 128) prefetch_l2(rf.grow + o);
-        if (ix.metric == HB_COSINE || ix.metric == HB_BQ_COSINE) rf.in = __ldg(&ix.hdr[s]);
+        if (ix.metric == HB_COSINE || ix.metric == HB_BQ_COSINE) rf.in = ix.hdr_uniform ? ix.hdr_value : __ldg(&ix.hdr[s]);
     }
 }
 
@@ -453,8 +456,6 @@ __device__ __noinline__ void team_help(const SearchParams& p, TeamShared& ts, Ro
     }
 }
 
-constexpr int MERGE_TILES = 8;  // heaps of up to 256 entries are merged through registers, larger ones tile by tile in place
-
 __device__ __forceinline__ u64 warp_min_u64(u64 v) {
     uint32_t hi = (uint32_t)(v >> 32);
     uint32_t mhi = __reduce_min_sync(FULL, hi);
@@ -473,40 +474,56 @@ struct ChunkUpdate {
     bool acc;       // this lane's point is accepted: pushed to the search queue
     bool pf;        // ... and passes the candidate filter: may enter the result set
     bool qskip;     // this lane's point was popped straight away by the caller: not pushed (it still enters `res`)
-    bool seq_done;  // large heaps: stage A already applied both updates one by one
     uint32_t bits, s;
 };
 
 __device__ __forceinline__ void heaps_stage_res(Ctx& c, ChunkUpdate& u, int ef) {
     const unsigned resm = __ballot_sync(FULL, u.acc && u.pf);
-    u.seq_done = false;
     // Pushing the keys one by one with `if len == ef { push_pop_max } else { push }` leaves the min(ef, len + m)
     // smallest of the union when len <= ef, and the whole union when len > ef (or for entry points).
     const int m_res = __popc(resm);
     int target = (u.mode == CH_EP || c.res_len > ef) ? c.res_len + m_res : min(ef, c.res_len + m_res);
     if (target > c.res_cap) { c.overflow = true; return; }
-    if (m_res) c.res_len = merge_any<false, false, MERGE_TILES>(c.res, c.res_len, u.acc && u.pf, ((u64)u.bits << 32) | u.s, target, 0u);
+    if (m_res) c.res_len = merge_insert<false>(c.res, c.res_len, u.acc && u.pf, ((u64)u.bits << 32) | u.s, target);
+}
+// The queue is a window [c.que, c.que + c.q_len) of its buffer with c.q_cap cells left from c.que on: entries that can
+// never be popped again (is_dead, judged against the UPDATED result set) form a prefix of the descending array and are
+// trimmed by moving the window's start, new dead ones are not pushed.  When the window hits the end of the buffer it is
+// moved back to the start.
+__device__ __forceinline__ void queue_rewind(Ctx& c) {
+    const int head = (int)c.p.q_cap - c.q_cap;
+    c.que -= head;
+    c.q_cap += head;
 }
 __device__ __forceinline__ void heaps_stage_queue(Ctx& c, const ChunkUpdate& u, int ef) {
-    if (u.seq_done || u.mode == CH_LINEAR || c.overflow) return;
+    if (u.mode == CH_LINEAR || c.overflow) return;
     const int lane = lane_id();
-    // Entries that can never be popped (is_dead, judged against the UPDATED result set) are not pushed, and old
-    // ones — they sit at the front of the descending array — are trimmed in the same pass.
     const bool prune = c.p.pass == 0 && !c.p.cancel_after && !c.p.no_trim && c.res_len >= ef && c.res_len > 0 && !(c.res[c.res_len - 1] >> 63);
     const uint32_t mb = prune ? (uint32_t)(c.res[c.res_len - 1] >> 32) : 0xffffffffu;
+    if (prune && c.q_len > 0 && (uint32_t)(c.que[0] >> 32) > mb) {
+        int lo = 1, hi = c.q_len;                  // first entry that is not dead (warp-uniform search)
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((uint32_t)(c.que[mid] >> 32) > mb) lo = mid + 1; else hi = mid;
+        }
+        c.que += lo; c.q_cap -= lo; c.q_len -= lo;
+    }
     const bool qhas = u.acc && !u.qskip && !(prune && !(u.bits >> 31) && u.bits > mb);
     const int mq = __popc(__ballot_sync(FULL, qhas));
     if (c.q_len + mq > c.q_cap) {
-        int d0 = 0;
-        if (prune) {
-            for (int i = lane; i < c.q_len; i += 32) d0 += (uint32_t)(c.que[i] >> 32) > mb;
-            d0 = __reduce_add_sync(FULL, d0);
+        const int head = (int)c.p.q_cap - c.q_cap;
+        if (c.q_len + mq > (int)c.p.q_cap) { c.overflow = true; return; }  // would have to drop a live entry
+        __syncwarp();
+        for (int base = 0; base < c.q_len; base += 32) {                     // a[i] -> a[i - head], bottom up
+            const int i = base + lane;
+            const u64 v = i < c.q_len ? c.que[i] : 0ull;
+            __syncwarp();
+            if (i < c.q_len) c.que[i - head] = v;
+            __syncwarp();
         }
-        if (c.q_len + mq - d0 > c.q_cap) { c.overflow = true; return; }  // would have to drop a live entry
+        queue_rewind(c);
     }
-    // nothing to insert and no dead entry at the front (they form a prefix of the descending array): the queue is unchanged
-    if (mq || (prune && c.q_len > 0 && (uint32_t)(c.que[0] >> 32) > mb))
-        c.q_len = merge_any<true, true, MERGE_TILES>(c.que, c.q_len, qhas, ((u64)u.bits << 32) | (uint32_t)(~u.s), c.q_cap, mb);
+    if (mq) c.q_len = merge_insert<true>(c.que, c.q_len, qhas, ((u64)u.bits << 32) | (uint32_t)(~u.s), c.q_cap);
 }
 
 // Visitor::visit — reader.rs:301-369 — and, with `linear`, the candidate loop of brute_force_search
@@ -531,6 +548,7 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
     const u64 NONE = ~0ull;
     c.res_len = 0;
     c.q_len = 0;
+    queue_rewind(c);
     c.cur_dist = c.cur_exp = c.cur_deg = 0;
     const uint32_t* list = linear ? c.p.cand_slots : eps;
     const uint32_t n_first = linear ? c.p.n_cand_slots : (eps ? n_eps : 1u);
@@ -547,7 +565,7 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
     bool pend = false;
     bool merge_deferred = false;   // the queue half of the pending chunk's merge runs after the next chunk's rows were requested (HB_EARLY_ROWS)
     ChunkUpdate u;
-    u.mode = CH_EP; u.acc = u.pf = u.qskip = u.seq_done = false; u.bits = u.s = 0;
+    u.mode = CH_EP; u.acc = u.pf = u.qskip = false; u.bits = u.s = 0;
     for (;;) {
         int mode;
         uint32_t s = 0, old = 0xffffffffu;
@@ -1031,8 +1049,8 @@ __device__ void run_query(const SearchParams& p, uint64_t qi, int slot_idx, u64*
 }
 
 // Shared memory of one warp: [row ring][ring barriers][query][heaps (pass 0 only)].
-template <int KIND>
-__global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, KIND == KIND_F32_WARP ? HB_MIN_BLOCKS_F32 : (KIND == KIND_F32_DIRECT ? HB_MIN_BLOCKS_DIRECT : (KIND == KIND_BIN ? HB_MIN_BLOCKS_BIN : 4))) hnsw_search_kernel(const __grid_constant__ SearchParams p) {
+template <int KIND, int MIN_BLOCKS>
+__global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, MIN_BLOCKS) hnsw_search_kernel(const __grid_constant__ SearchParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp_in_block = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
@@ -1307,20 +1325,27 @@ size_t search_smem_per_warp(const SearchParams& p) {
 }
 
 typedef void (*search_kernel_t)(const SearchParams);
-// the kernel variant a call runs: f32 warp rows without a ring are gathered directly
-static int variant_of(const SearchParams& p) { return (p.ix.kind == KIND_F32_WARP && p.ring_slots == 0) ? KIND_F32_DIRECT : p.ix.kind; }
-static search_kernel_t kernel_for(int kind) {
-    switch (kind) {
-        case KIND_F32_WARP: return hnsw_search_kernel<KIND_F32_WARP>;
-        case KIND_F32_DIRECT: return hnsw_search_kernel<KIND_F32_DIRECT>;
-        case KIND_F32_LANE: return hnsw_search_kernel<KIND_F32_LANE>;
-        default: return hnsw_search_kernel<KIND_BIN>;
+// The kernel variant a call runs: the three row kinds, f32 warp rows without a ring (gathered directly), and the f32 ring
+// kernel compiled for one more resident CTA per SM (fewer registers) for rows whose rings leave room for it.
+constexpr int VAR_F32_RING_SHORT = 4, N_VARIANTS = 5;
+static int variant_of(const SearchParams& p) {
+    if (p.ix.kind != KIND_F32_WARP) return p.ix.kind;
+    if (p.ring_slots == 0) return KIND_F32_DIRECT;
+    return p.ring_short ? VAR_F32_RING_SHORT : KIND_F32_WARP;
+}
+static search_kernel_t kernel_for(int variant) {
+    switch (variant) {
+        case KIND_F32_WARP: return hnsw_search_kernel<KIND_F32_WARP, HB_MIN_BLOCKS_F32>;
+        case VAR_F32_RING_SHORT: return hnsw_search_kernel<KIND_F32_WARP, HB_MIN_BLOCKS_F32_SHORT>;
+        case KIND_F32_DIRECT: return hnsw_search_kernel<KIND_F32_DIRECT, HB_MIN_BLOCKS_DIRECT>;
+        case KIND_F32_LANE: return hnsw_search_kernel<KIND_F32_LANE, 4>;
+        default: return hnsw_search_kernel<KIND_BIN, HB_MIN_BLOCKS_BIN>;
     }
 }
 static void set_kernel_attrs() {
     static bool attr_set = false;
     if (!attr_set) {
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < N_VARIANTS; ++k)
             if (cudaFuncSetAttribute(kernel_for(k), cudaFuncAttributeMaxDynamicSharedMemorySize, SEARCH_MAX_SMEM) != cudaSuccess) {
                 fprintf(stderr, "[hb] cudaFuncSetAttribute(MaxDynamicSharedMemorySize = %d) failed for search kernel %d: %s\n", SEARCH_MAX_SMEM, k, cudaGetErrorString(cudaGetLastError()));
             }
@@ -1351,7 +1376,7 @@ hb_status launch_search(const SearchParams& fast, const SearchParams& slow, int 
         cudaMemsetAsync(fast.n_overflow, 0, sizeof(uint32_t), stream);
         size_t smem = search_smem_per_warp(fast) * wpb;
         // a batch smaller than the resident warps: one CTA per query while CTAs last (its other warps become helpers)
-        const bool team = variant_of(fast) == KIND_F32_WARP && fast.team;
+        const bool team = fast.ix.kind == KIND_F32_WARP && fast.ring_slots != 0 && fast.team;
         uint64_t need = team ? (uint64_t)fast.n_work : ((uint64_t)fast.n_work + wpb - 1) / wpb;
         int blocks = (uint64_t)blocks_fast > need ? (int)need : blocks_fast;
         if (blocks < 1) blocks = 1;

@@ -65,101 +65,29 @@ __device__ __forceinline__ void topk_insert(u64* a, int& len, int cap, u64 key) 
 }
 
 // ---- batched merge -------------------------------------------------------------------------------------
-// Merge up to 32 new keys (lane L contributes `key` iff `has`) into the sorted array a[0..len) in ONE pass:
-// every lane binary-searches the slot of its own key, the old entries are pulled into registers, each
-// entry's displacement is the number of new keys that sort before it, then everything is written back.
-// Equivalent to inserting the keys one after the other (all keys are distinct), at the cost of one insertion.
-//   DESC       array is descending (search queue, next pop at the end) instead of ascending (result set)
-//   drop_above (TRIM only) old entries whose distance bits exceed it are dropped: they sit at the front of a
-//              descending array
-//   keep       final length is capped to `keep` (the entries that sort last are dropped)
-// Needs len <= 32 * MAX_TILES.  Returns the new length.
-#ifdef HB_MERGE_NOINLINE
-#define HB_MERGE_INLINE __noinline__
-#else
-#define HB_MERGE_INLINE __forceinline__
+// Merge up to 32 new keys (lane L contributes `key` iff `has`) into the sorted array a[0..len), in place, in ONE pass,
+// for arrays of any length in shared or global memory.  Every lane binary-searches the slot of its own key and ranks it
+// among the new keys: old position + rank is the key's FINAL position, and the final positions of the new keys are a
+// bit mask F over the new array.  The old entries then fill the cells F leaves free, in order: cell j of the new
+// array takes old entry j - |{new keys placed below j}| — one popcount per cell instead of one comparison per (cell, new
+// key) pair.  Cells are moved in blocks of MERGE_BLOCK tiles of 32, from the top block down (an entry only ever moves up):
+// the F words of a block come from MERGE_BLOCK independent warp reductions, then all loads of the block are issued, then
+// all its stores — one shared-memory round trip per block (2 tiles: measured best on all three workloads against 1, 3, 4 and 8).  Tiles below the
+// first insertion point are not touched.  Equivalent to inserting the keys one after the other (all keys are distinct).
+//   DESC   array is descending (search queue, next pop at the end) instead of ascending (result set)
+//   keep   final length is capped to `keep` (the entries that sort last are dropped)
+// Returns the new length.
+#ifndef HB_MERGE_BLOCK
+#define HB_MERGE_BLOCK 2
 #endif
-template <bool DESC, bool TRIM, int MAX_TILES>
-__device__ HB_MERGE_INLINE int merge_batch(u64* a, int len, bool has, u64 key, int keep, uint32_t drop_above) {
+constexpr int MERGE_BLOCK = HB_MERGE_BLOCK;
+template <bool DESC>
+__device__ __forceinline__ int merge_insert(u64* a, int len, bool has, u64 key, int keep) {
     const int lane = lane_id();
     const unsigned hm = __ballot_sync(FULL, has);
-    int pos = 0x7fffffff;
-    if (has) {
-        int lo = 0, hi = len;
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            u64 x = a[mid];
-            bool before = DESC ? (x > key) : (x < key);
-            if (before) lo = mid + 1; else hi = mid;
-        }
-        pos = lo;
-    }
-    // Entries below the smallest insertion point do not move (unless the front is trimmed): their tiles are neither
-    // loaded nor stored.  Dead entries form a prefix of a descending array, so a[0] tells whether there is any.
-    const bool trim = TRIM && len > 0 && (uint32_t)(a[0] >> 32) > drop_above;
-    const int t0 = trim ? 0 : (int)(__reduce_min_sync(FULL, (unsigned)pos) >> 5);
-    u64 v[MAX_TILES];
-    int sh[MAX_TILES];
-    int d = 0;
-#pragma unroll
-    for (int t = 0; t < MAX_TILES; ++t) {
-        int i = t * 32 + lane;
-        v[t] = 0ull;
-        sh[t] = 0;
-        if (t >= t0 && t * 32 < len) {  // warp-uniform
-            if (i < len) v[t] = a[i];
-            if (TRIM) { if (trim) d += __popc(__ballot_sync(FULL, i < len && (uint32_t)(v[t] >> 32) > drop_above)); }
-        }
-    }
-    if (!has) pos = 0;
-    int rank = 0;
-    for (unsigned m = hm; m; m &= m - 1) {
-        int src = __ffs(m) - 1;
-        u64 kb = __shfl_sync(FULL, key, src);
-        int pb = __shfl_sync(FULL, pos, src);
-        rank += DESC ? (kb > key) : (kb < key);
-#pragma unroll
-        for (int t = 0; t < MAX_TILES; ++t)
-            if (t >= t0 && t * 32 < len) sh[t] += (pb <= t * 32 + lane);
-    }
-    __syncwarp();
-    const int new_len = min(len + __popc(hm) - d, keep);
-#pragma unroll
-    for (int t = 0; t < MAX_TILES; ++t) {
-        int i = t * 32 + lane;
-        int j = i + sh[t] - d;
-        if (t >= t0 && t * 32 < len && i < len && j >= 0 && j < new_len) a[j] = v[t];
-    }
-    if (has) {
-        int j = pos + rank - d;
-        if (j >= 0 && j < new_len) a[j] = key;
-    }
-    __syncwarp();
-    return new_len;
-}
-
-// The same merge for arrays of any length (heaps beyond 32 * MAX_TILES entries: large ef, the global-memory pass): the
-// old entries are moved tile by tile from the top down, each by the number of new keys that sort before it; tiles below
-// the first insertion point are not touched.  A dead prefix (TRIM) is compacted away first, bottom up.
-template <bool DESC, bool TRIM>
-__device__ __noinline__ int merge_batch_large(u64* a, int len, bool has, u64 key, int keep, uint32_t drop_above) {
-    const int lane = lane_id();
-    if (TRIM && len > 0 && (uint32_t)(a[0] >> 32) > drop_above) {
-        int d = 0;
-        for (int i = lane; i < len; i += 32) d += (uint32_t)(a[i] >> 32) > drop_above;
-        d = __reduce_add_sync(FULL, d);
-        for (int base = d; base < len; base += 32) {  // a[i] -> a[i - d], bottom up
-            const int i = base + lane;
-            const u64 v = i < len ? a[i] : 0ull;
-            __syncwarp();
-            if (i < len) a[i - d] = v;
-            __syncwarp();
-        }
-        len -= d;
-    }
-    const unsigned hm = __ballot_sync(FULL, has);
-    if (!hm) return min(len, keep);
-    int pos = 0x7fffffff;
+    const int new_len = min(len + __popc(hm), keep);
+    if (!hm || new_len <= 0) return max(new_len, 0);
+    unsigned fp = 0xffffffffu;                      // final position of this lane's key
     if (has) {
         int lo = 0, hi = len;
         while (lo < hi) {
@@ -168,39 +96,45 @@ __device__ __noinline__ int merge_batch_large(u64* a, int len, bool has, u64 key
             const bool before = DESC ? (x > key) : (x < key);
             if (before) lo = mid + 1; else hi = mid;
         }
-        pos = lo;
+        fp = (unsigned)lo;
     }
-    const int t0 = (int)(__reduce_min_sync(FULL, (unsigned)pos) >> 5);
-    if (!has) pos = 0x7fffffff;
-    int rank = 0;
-    for (unsigned m = hm; m; m &= m - 1) {
-        const u64 kb = __shfl_sync(FULL, key, __ffs(m) - 1);
-        rank += DESC ? (kb > key) : (kb < key);
+    {
+        int rank = 0;
+        for (unsigned m = hm; m; m &= m - 1) {
+            const u64 kb = __shfl_sync(FULL, key, __ffs(m) - 1);
+            rank += DESC ? (kb > key) : (kb < key);
+        }
+        if (has) fp += (unsigned)rank;
     }
-    const int new_len = min(len + __popc(hm), keep);
-    __syncwarp();
-    for (int t = (len - 1) >> 5; t >= t0 && len > 0; --t) {
-        const int i = t * 32 + lane;
-        const u64 v = i < len ? a[i] : 0ull;
-        int sh = 0;
-        for (unsigned m = hm; m; m &= m - 1) sh += __shfl_sync(FULL, pos, __ffs(m) - 1) <= i;
-        __syncwarp();  // the tile is in registers: its cells (and the ones above, already moved) may be overwritten
-        if (i < len && i + sh < new_len) a[i + sh] = v;
+    const int t0 = (int)(__reduce_min_sync(FULL, fp) >> 5);
+    const int t_top = (new_len - 1) >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int tb = t_top - (t_top - t0) % MERGE_BLOCK; tb >= t0; tb -= MERGE_BLOCK) {   // blocks [tb, tb + MERGE_BLOCK), top down; the lowest starts at t0
+        int below = __popc(__ballot_sync(FULL, fp < (unsigned)(tb << 5)));             // new keys placed under the block
+        u64 v[MERGE_BLOCK];
+        unsigned moved = 0;
+#pragma unroll
+        for (int i = 0; i < MERGE_BLOCK; ++i) {
+            v[i] = 0ull;
+            if (tb + i <= t_top) {                  // warp-uniform: only the top block can be short
+                const unsigned f = __reduce_or_sync(FULL, (fp >> 5) == (unsigned)(tb + i) ? 1u << (fp & 31u) : 0u);
+                const int j = ((tb + i) << 5) + lane;
+                const int src = j - below - __popc(f & lt);
+                below += __popc(f);
+                const bool mv = j < new_len && !((f >> lane) & 1u) && src != j;
+                if (mv) v[i] = a[src];
+                moved |= (unsigned)mv << i;
+            }
+        }
+        __syncwarp();                               // every lane holds its entries of the block: the cells may be overwritten
+#pragma unroll
+        for (int i = 0; i < MERGE_BLOCK; ++i)
+            if ((moved >> i) & 1u) a[((tb + i) << 5) + lane] = v[i];
         __syncwarp();
     }
-    if (has) {
-        const int j = pos + rank;
-        if (j < new_len) a[j] = key;
-    }
+    if (fp < (unsigned)new_len) a[fp] = key;
     __syncwarp();
     return new_len;
-}
-
-// merge of up to 32 keys into a sorted array of any length
-template <bool DESC, bool TRIM, int MAX_TILES>
-__device__ __forceinline__ int merge_any(u64* a, int len, bool has, u64 key, int keep, uint32_t drop_above) {
-    if (len <= 32 * MAX_TILES) return merge_batch<DESC, TRIM, MAX_TILES>(a, len, has, key, keep, drop_above);
-    return merge_batch_large<DESC, TRIM>(a, len, has, key, keep, drop_above);
 }
 
 }  // namespace hb

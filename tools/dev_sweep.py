@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--trace", default="", help="HB_TRACE builds: save the event trace of one warp over one step (.npy)")
     ap.add_argument("--nq", type=int, default=0, help="override the batch size")
+    ap.add_argument("--nq-list", default="", help="also time these batch sizes (prefixes of the batch), comma separated")
     ap.add_argument("--device-build", action="store_true", help="build the graph on the device (seconds) instead of with the oracle builder")
     args = ap.parse_args()
     import torch
@@ -43,24 +44,38 @@ def main():
     dev = torch.device("cuda", 0)
     threads = len(os.sched_getaffinity(0))
     log = lambda m: print(f"[sweep] {m}", file=sys.stderr, flush=True)
-    x = bench.gen_vectors(w["gen"], w["n"], w["dims"], w["seed"], dev)
+    binary = "binary" in w["metric"] or w["metric"] == "hamming"
     q = bench.gen_vectors(w["gen"], w["nq"], w["dims"], w["seed"] + 1, dev)
-    x_host, q_host = x.cpu().numpy(), q.cpu().numpy()
-    del x
-    if args.device_build:
-        from oracle.oracle import OracleDb
+    q_host = q.cpu().numpy()
+    if binary:
+        # the same items bench.run_other_workload builds: quantized on the GPU chunk by chunk, graph built on the device
         ids = np.arange(w["n"], dtype=np.uint32)
-        db = OracleDb(w["metric"], w["dims"])
-        db.add_items(ids, x_host)
-        rd = hb.Reader.build(w["metric"], w["dims"], ids, x_host, db.headers() if w["metric"] == "cosine" else None, M=16, M0=32, ef_construction=100, seed=42)
-        from oracle import oracle as O
-        for l, (off, nbr) in enumerate(rd.layers()):
-            O.lib().orc_db_set_csr(db.h, l, O._p(off), O._p(nbr), len(nbr))
-        db.set_entry_points(rd.entry_points(), rd.max_level())
+        rows = np.empty((w["n"], w["dims"] // 64), np.uint64)
+        chunk = 250_000
+        for s0 in range(0, w["n"], chunk):
+            m = min(chunk, w["n"] - s0)
+            rows[s0:s0 + m] = bench.quantize_bq(bench.gen_vectors(w["gen"], m, w["dims"], w["seed"] * 1000 + s0 // chunk, dev))
+        hdr = np.full(w["n"], np.float32(np.sqrt(np.float32(w["dims"]))), np.float32)
+        rd = hb.Reader.build(w["metric"], w["dims"], ids, rows, hdr, M=16, M0=32, ef_construction=100, seed=42)
+        db = bench.oracle_from_reader(rd, w["metric"], w["dims"], rows, ids)
     else:
-        db = bench.build_or_load_graph(w, x_host, dev.type, threads, log)
-        rd = hb.Reader.from_arrays(w["metric"], w["dims"], db.ids(), db.rows(), db.headers(), db.layers(), db.entry_points,
-                                   db.max_level, device=0)
+        x = bench.gen_vectors(w["gen"], w["n"], w["dims"], w["seed"], dev)
+        x_host = x.cpu().numpy()
+        del x
+        if args.device_build:
+            from oracle.oracle import OracleDb
+            ids = np.arange(w["n"], dtype=np.uint32)
+            db = OracleDb(w["metric"], w["dims"])
+            db.add_items(ids, x_host)
+            rd = hb.Reader.build(w["metric"], w["dims"], ids, x_host, db.headers() if w["metric"] == "cosine" else None, M=16, M0=32, ef_construction=100, seed=42)
+            from oracle import oracle as O
+            for l, (off, nbr) in enumerate(rd.layers()):
+                O.lib().orc_db_set_csr(db.h, l, O._p(off), O._p(nbr), len(nbr))
+            db.set_entry_points(rd.entry_points(), rd.max_level())
+        else:
+            db = bench.build_or_load_graph(w, x_host, dev.type, threads, log)
+            rd = hb.Reader.from_arrays(w["metric"], w["dims"], db.ids(), db.rows(), db.headers(), db.layers(), db.entry_points,
+                                       db.max_level, device=0)
     k, nq = w["k"], w["nq"]
     ef_raw = max(args.ef, k)
     dq = q.contiguous()
@@ -82,20 +97,21 @@ def main():
     combos = list(itertools.product(*vals)) if keys else [()]
     want = None
     results = []
-    for combo in combos:
+    nq_full = nq
+    for nq, combo in [(n_, c_) for n_ in [nq_full] + [int(v) for v in args.nq_list.split(",") if v] for c_ in combos]:
         for kname, v in zip(keys, combo):
             L.hb_tune(kname.encode(), v)
         step(ctr=True)
         torch.cuda.synchronize()
-        ctr = d_ctr.cpu().numpy().astype(np.uint64)
+        ctr = d_ctr.cpu().numpy().astype(np.uint64)[:nq]
         alg, vec = bench.algorithmic_bytes(ctr, w)
         n_par = min(args.parity, nq)
-        if want is None:
+        if want is None or len(want[2]) < n_par:
             want = db.search_by_vector(q_host[:n_par], k, ef=ef_raw, n_threads=threads, counters=True)
         ids = d_ids[:n_par].cpu().numpy().view(np.uint32)
         dd = d_dist[:n_par].cpu().numpy()
         ln = d_len[:n_par].cpu().numpy().view(np.uint32)
-        ok = bool(np.array_equal(ln, want[2]) and np.array_equal(ids, want[0]) and np.array_equal(dd.view(np.uint32), want[1].view(np.uint32)))
+        ok = bool(np.array_equal(ln, want[2][:n_par]) and np.array_equal(ids, want[0][:n_par]) and np.array_equal(dd.view(np.uint32), want[1][:n_par].view(np.uint32)))
         ok_ctr = bool(np.array_equal(ctr[:n_par, :6], want[3][:n_par, :6].astype(np.uint64))) if len(want) > 3 else None
         for _ in range(3):
             step()
@@ -111,7 +127,7 @@ def main():
         ms = e0.elapsed_time(e1) / args.steps
         ph = np.zeros(16, np.uint64)
         L.hb_debug_phases(ph.ctypes.data)
-        r = dict(tune=dict(zip(keys, combo)), ms=round(ms, 3), qps=round(nq / ms * 1e3), gbs=round(alg / ms / 1e6, 1), parity=ok, counters=ok_ctr,
+        r = dict(nq=nq, tune=dict(zip(keys, combo)), ms=round(ms, 4), qps=round(nq / ms * 1e3), gbs=round(alg / ms / 1e6, 1), parity=ok, counters=ok_ctr,
                  slow=int((ctr[:, 6] & 4).astype(bool).sum()), evals_per_q=float(ctr[:, :2].sum() / nq), exp_per_q=float(ctr[:, 2:4].sum() / nq))
         if ph.sum():
             tot = float(ph[7]) or 1.0
