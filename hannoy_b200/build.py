@@ -28,6 +28,9 @@ for _b in (4, 5, 6, 7, 8):   # dev: occupancy the binary / f32 ring kernels are 
     VARIANTS[f"g2bin{_b}"] = [f"-DHB_MIN_BLOCKS_BIN={_b}", "-DHB_MERGE_BLOCK=2"]
     VARIANTS[f"f32b{_b}"] = [f"-DHB_MIN_BLOCKS_F32={_b}"]
     VARIANTS[f"g2f32b{_b}"] = [f"-DHB_MIN_BLOCKS_F32={_b}", "-DHB_MERGE_BLOCK=2"]
+VARIANTS["nospec"] = ["-DHB_SPEC_VIS=0"]
+VARIANTS["nospecbin"] = ["-DHB_SPEC_VIS_BIN=0"]
+VARIANTS["nodedupe"] = ["-DHB_SPEC_DEDUPE=0"]
 for _g in (1, 2, 3, 8):
     VARIANTS[f"g{_g}"] = [f"-DHB_MERGE_BLOCK={_g}"]
 

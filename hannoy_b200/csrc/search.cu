@@ -43,6 +43,15 @@
 #ifndef HB_EARLY_ROWS
 #define HB_EARLY_ROWS 1  // layer-0 deferred pops: request the rows of an expansion before merging the previous chunk into the heaps
 #endif
+#ifndef HB_SPEC_VIS
+#define HB_SPEC_VIS 1      // prefetch the visited-set words of the expected next expansion's neighbours (C2 +10 %, C3 small batches +7 %)
+#endif
+#ifndef HB_SPEC_DEDUPE
+#define HB_SPEC_DEDUPE 1
+#endif
+#ifndef HB_SPEC_VIS_BIN
+#define HB_SPEC_VIS_BIN 1  // ... in the binary kernel too
+#endif
 #ifndef HB_MIN_BLOCKS_F32
 #define HB_MIN_BLOCKS_F32 3  // resident CTAs per SM the f32 ring kernel is compiled for (register budget): long rows, shared memory allows no more
 #endif
@@ -269,28 +278,38 @@ __device__ __forceinline__ float rows_finish(Ctx& c, const RowsInFlight& rf, uin
     } else if (KIND == KIND_F32_WARP) {
         // slot group g is re-posted as soon as its ROW_GROUP rows were consumed
         const int S = (int)c.ring.slots;
+        const bool g4 = c.p.gather4 != 0;
+        const uint32_t stride = c.ring.stride;
         int slot0 = 0;
+        const uint8_t* gp = c.ring.ptr;            // first slot of the group being consumed
         float myraw = 0.0f;
         for (int r0 = 0; r0 < rf.n_live; r0 += ROW_GROUP) {
             const int g = min(ROW_GROUP, rf.n_live - r0);
             const uint8_t* rowp[ROW_GROUP];
+            if (g4) {
+                c.ring.wait(slot0); TR(c, TR_ROWWAIT)   // a gathered group completes on its first slot's barrier; rows past the last read as zeros
 #pragma unroll
-            for (int r = 0; r < ROW_GROUP; ++r) {
-                if (r < g && (r == 0 || !c.p.gather4)) { c.ring.wait(slot0 + r); TR(c, TR_ROWWAIT) }   // a gathered group completes on its first slot's barrier
-                rowp[r] = c.ring.ptr + (size_t)(slot0 + (r < g ? r : 0)) * c.ring.stride;
+                for (int r = 0; r < ROW_GROUP; ++r) rowp[r] = gp + r * stride;
+            } else {
+#pragma unroll
+                for (int r = 0; r < ROW_GROUP; ++r) {
+                    if (r < g) { c.ring.wait(slot0 + r); TR(c, TR_ROWWAIT) }
+                    rowp[r] = gp + (r < g ? r : 0) * stride;
+                }
             }
             // row r's sum comes back on lane group_owner(r); the lane that owns the row picks it up
             float red = (ix.metric == HB_COSINE) ? warp_rows_group<ROW_GROUP, true, true>(ix, c.qs, rowp) : warp_rows_group<ROW_GROUP, false, true>(ix, c.qs, rowp);
             __syncwarp();  // every lane has read the group's slots: they may be overwritten
-            const int nxt = rf.rank - r0 - S;
-            if (c.p.gather4) {
+            const int mr = rf.rank - r0;
+            const int nxt = mr - S;
+            if (g4) {
                 if (rf.has && nxt == 0) c.ring.post_gather4(slot0, c.p.rows_tmap, s, rf.g1, rf.g2, rf.g3);
             } else if (rf.has && nxt >= 0 && nxt < g) c.ring.post(slot0 + nxt, rf.grow, ix.row_stride);
-            const int mr = rf.rank - r0;
-            const float got = __shfl_sync(FULL, red, group_owner<ROW_GROUP>(mr >= 0 && mr < ROW_GROUP ? mr : 0));
+            const float got = __shfl_sync(FULL, red, group_owner<ROW_GROUP>(mr & (ROW_GROUP - 1)));
             if (rf.has && mr >= 0 && mr < g) myraw = got;
             slot0 += ROW_GROUP;
-            if (slot0 >= S) slot0 = 0;
+            gp += ROW_GROUP * stride;
+            if (slot0 >= S) { slot0 = 0; gp = c.ring.ptr; }
             TR(c, TR_GROUP)
         }
         if (rf.has) mine = finish_f32(ix.metric, myraw, c.qn, rf.in);
@@ -560,6 +579,7 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
     uint32_t cont_cs = 0;                                    // node whose fixed-stride list is being continued (csr_pos = 32, csr_end = xstride)
     const bool defer = nbrx && c.p.pass == 0 && c.p.defer && !linear && !c.p.no_trim;  // a linear scan pops nothing (reader.rs:683-705)
     uint32_t spec_cs = 0xffffffffu, spec_adj = 0xffffffffu;  // adjacency line requested ahead of its pop
+    uint32_t spec_pf = 0xffffffffu;                          // node whose neighbours' visited-set words were already prefetched
     uint32_t csr_pos = 0, csr_end = 0;                       // rest of the CSR list being expanded
     float f_max = FLT_MAX;
     bool pend = false;
@@ -746,6 +766,15 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
         if (!lm) { if (bail) break; continue; }
         // ---- gather: finish, distances ----
         float dist = rows_finish<KIND>(c, rf, s);
+#if HB_SPEC_VIS
+        // the adjacency line requested ahead has landed by now: pull the visited-set words of ITS neighbours into L2, so that
+        // the atomics of the next expansion — when it is the one expected — are answered by L2 instead of DRAM
+        // (once per expected node: it stays the expected one for as long as freshly accepted points are popped ahead of it)
+        if ((HB_SPEC_VIS_BIN || KIND != KIND_BIN) && nbrx && spec_cs != 0xffffffffu && (!HB_SPEC_DEDUPE || spec_cs != spec_pf)) {
+            if (spec_adj != 0xffffffffu) prefetch_l2(&c.vis[spec_adj >> 5]);
+            spec_pf = spec_cs;
+        }
+#endif
         if (l01) PH_ADD(c, PH_ROWS)
         if (KIND == KIND_F32_WARP && helpers_used) dist = team_collect(c, lm, helpers_used, per, dist);
         if (bail) break;
