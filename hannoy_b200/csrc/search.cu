@@ -769,8 +769,9 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
 #if HB_SPEC_VIS
         // the adjacency line requested ahead has landed by now: pull the visited-set words of ITS neighbours into L2, so that
         // the atomics of the next expansion — when it is the one expected — are answered by L2 instead of DRAM
-        // (once per expected node: it stays the expected one for as long as freshly accepted points are popped ahead of it)
-        if ((HB_SPEC_VIS_BIN || KIND != KIND_BIN) && nbrx && spec_cs != 0xffffffffu && (!HB_SPEC_DEDUPE || spec_cs != spec_pf)) {
+        // (binary kernel: once per expected node — it stays the expected one for as long as freshly accepted points are popped ahead of
+        // it; the f32 kernels measure faster when the hint is repeated every expansion: C2 5.08 vs 5.67 ms, C3 single query 0.70 vs 0.78 ms)
+        if ((HB_SPEC_VIS_BIN || KIND != KIND_BIN) && nbrx && spec_cs != 0xffffffffu && (KIND != KIND_BIN || !HB_SPEC_DEDUPE || spec_cs != spec_pf)) {
             if (spec_adj != 0xffffffffu) prefetch_l2(&c.vis[spec_adj >> 5]);
             spec_pf = spec_cs;
         }
