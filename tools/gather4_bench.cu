@@ -151,7 +151,7 @@ int main() {
     const uint64_t n128 = bytes / 128;
     for (int kind = 0; kind < 2; ++kind)
         for (uint32_t live : {14u, 32u})
-            for (int wps : {16, 24, 32, 48, 64}) {
+            for (int wps : {8, 12, 16, 16, 20, 24, 32, 48, 64}) {
                 int blocks = sms * wps / 4;
                 uint32_t iters = (uint32_t)((6ull << 30) / ((uint64_t)blocks * 4 * live * 128));
                 auto launch = [&](uint32_t it) {
