@@ -42,6 +42,9 @@ WORKLOADS = {
                desc="1M x 768 f32 Cosine (text-embedding shaped), 10k-query batch, top-10"),
     "c4s": dict(metric="binary quantized cosine", n=1_000_000, dims=1024, nq=100_000, k=100, efs=[100, 200, 400], gen="lowrank", seed=7,
                 desc="1M x 1024 BinaryQuantizedCosine codes (scaled-down config 4), 100k-query batch, top-100"),
+    # config 4 at full size (tools/c4_full.py, tools/dev_sweep.py; not part of the default run: the 10M-item device build alone takes 22 s)
+    "c4": dict(metric="binary quantized cosine", n=10_000_000, dims=1024, nq=100_000, k=100, efs=[100, 200, 400, 800], gen="lowrank", seed=7,
+               desc="10M x 1024 BinaryQuantizedCosine codes (config 4), 100k-query batch, top-100"),
     # config 5, scaled: index sharded by item id (id % n_gpus), every GPU searches ALL queries on its shard, per-shard
     # top-k exchanged over NVLink and merged.  n = items PER SHARD.
     "c5s": dict(metric="cosine", n=250_000, dims=768, nq=20_000, k=10, efs=[128], gen="lowrank", seed=9, sharded=True,
@@ -366,13 +369,36 @@ def load_peaks():
         return {}
 
 
-def roofline_of(alg_bytes, vec_bytes, ms, peaks, traffic=None, traffic_src=None):
+def gather_ceiling(row_bytes):
+    """What random gathers of rows of this length reach on a B200 when nothing else is done: the best figure of the committed
+    microbenchmarks (tools/gather_bench.cu, tools/gather4_bench.cu) for the nearest measured row length.  The copy peak is the
+    roofline of long rows only: the memory system serves a bounded number of random rows per second whatever their length."""
+    best, src = {}, {}
+    for f in ("r01_gather_microbench.json", "r02_gather4_microbench.json"):
+        try:
+            for r in json.load(open(os.path.join(ROOT, "profiles", f)))["results"]:
+                if not r.get("err") and r["gbs"] > best.get(r["row_bytes"], 0):
+                    best[r["row_bytes"]], src[r["row_bytes"]] = r["gbs"], f"profiles/{f}: {r['kind']}, {r['warps_per_sm']} warps/SM"
+        except Exception:
+            pass
+    if not best:
+        return None
+    rb = min(best, key=lambda b: abs(np.log(b / row_bytes)))
+    return {"gbs": best[rb], "measured_row_bytes": rb, "source": src[rb]}
+
+
+def roofline_of(alg_bytes, vec_bytes, ms, peaks, traffic=None, traffic_src=None, row_bytes=None):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (ms / 1e3) / 1e9
-    return {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-            "traffic": traffic, "traffic_source": traffic_src, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
-            "algorithmic_bytes_per_step": int(alg_bytes), "gathered_vector_bytes_per_step": int(vec_bytes),
-            "kernel": "hnsw_search_kernel", "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)}
+    r = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+         "traffic": traffic, "traffic_source": traffic_src, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
+         "algorithmic_bytes_per_step": int(alg_bytes), "gathered_vector_bytes_per_step": int(vec_bytes),
+         "kernel": "hnsw_search_kernel", "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)}
+    g = gather_ceiling(row_bytes) if row_bytes else None
+    if g:
+        g["frac"] = round(achieved / g["gbs"], 4)
+        r["random_gather_ceiling"] = g
+    return r
 
 
 def cpu_baseline_of(db, q_host, k, ef_raw, threads, n_cpu, ef_pick):
@@ -423,7 +449,7 @@ def run_other_workload(name, dev, local_rank, threads, log, steps=5):
     rec = {"workload": w["desc"], "graph": f"built on the device (hb_index_build_graph) in {st.get('build_call_ms', 0) / 1e3:.1f}s", "value": round(nq / ms * 1e3, 1), "unit": "queries/s",
            "ms_per_step": round(ms, 4), "steps": steps, "ef_search": ef_pick, "recall_at_k": sweep[ef_pick], "recall_sweep": sweep,
            "parity_vs_oracle": "bit-exact (ids, distance bits, traversal counters; 64 queries)" if parity_ok else "MISMATCH",
-           "roofline": roofline_of(alg, vec, ms, load_peaks()) if w["n"] * w["dims"] > (1 << 26) else "index fits L2: HBM fraction not meaningful",
+           "roofline": roofline_of(alg, vec, ms, load_peaks(), row_bytes=rows.shape[1] * rows.itemsize) if w["n"] * w["dims"] > (1 << 26) else "index fits L2: HBM fraction not meaningful",
            "cpu_baseline": cpu_baseline_of(db, q_host, k, ef_raw, threads, 1000 if k <= 10 else 300, ef_pick)}
     log(f"{name}: {rec['value']:.0f} QPS at ef={ef_pick} recall {sweep[ef_pick]} parity {parity_ok} ({time.time() - t0:.1f}s)")
     rd.close()
@@ -657,7 +683,7 @@ def main():
                     "batches_in_flight": 2, "one_batch_at_a_time": round(nq / t_serial, 1),
                     "note": "hb_search_by_vector on pinned host buffers (per rank: its slice of the batch); 2 host threads submit whole batches concurrently"},
             "gpu_launches": int(launches),
-            "roofline": roofline_of(alg_bytes, vec_bytes, ms_mine, peaks, traffic, traffic_src),
+            "roofline": roofline_of(alg_bytes, vec_bytes, ms_mine, peaks, traffic, traffic_src, row_bytes=4 * w["dims"]),
             "cpu_baseline": cpu_baseline_of(db, q_host, k, ef_raw, threads, 2000, ef_pick),
             "latency": lat,
         }

@@ -21,7 +21,7 @@ FLAGS = [
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false", "-split-compile", "0",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function",
 ]
-VARIANTS = {"": [], "phases": ["-DHB_PHASES"], "trace": ["-DHB_TRACE"], "rg2": ["-DHB_ROW_GROUP=2"],
+VARIANTS = {"": [], "phases": ["-DHB_PHASES"], "trace": ["-DHB_TRACE"], "rg2": ["-DHB_ROW_GROUP=2"], "rg8": ["-DHB_ROW_GROUP=8"],
             "late": ["-DHB_EARLY_ROWS=0"], "adjtop": ["-DHB_ADJ_PREFETCH_ALL=0"]}
 for _b in (4, 5, 6, 7, 8):   # dev: occupancy the binary / f32 ring kernels are compiled for, heap-merge block size
     VARIANTS[f"bin{_b}"] = [f"-DHB_MIN_BLOCKS_BIN={_b}"]

@@ -703,7 +703,7 @@ static hb_status run_search(const hb_index* ix, Workspace* w, SearchParams base,
         base.ring_slots = slots;
         base.ring_stride = d.row_stride;
         base.ring_short = tunable("ring_short", short_rows ? 1 : 0);
-        if (ix->have_rows_tmap && ROW_GROUP == 4 && tunable("gather4", 1)) { base.gather4 = 1; std::memcpy(base.rows_tmap, ix->rows_tmap, 128); }
+        if (ix->have_rows_tmap && ROW_GROUP % 4 == 0 && tunable("gather4", 1)) { base.gather4 = 1; std::memcpy(base.rows_tmap, ix->rows_tmap, 128); }
         SearchParams probe = base;
         probe.pass = 1;
         if (search_smem_per_warp(probe) * SEARCH_WARPS_PER_BLOCK > (size_t)SEARCH_MAX_SMEM) {
@@ -725,6 +725,10 @@ static hb_status run_search(const hb_index* ix, Workspace* w, SearchParams base,
     }
     fast.pass = 0;
     int bps_fast = search_blocks_per_sm(fast);
+    if (d.kind == KIND_BIN && bps_fast > 0 && bps_fast <= 4 && tunable("bin_wide", 1)) {
+        fast.bin_wide = 1;                 // shared memory, not registers, limits the occupancy: take the instantiation that spills nothing
+        bps_fast = search_blocks_per_sm(fast);
+    }
     if (bps_fast == 0) {
         fast.res_cap = 0; fast.q_cap = 0;  // every query takes the global-memory pass
     }

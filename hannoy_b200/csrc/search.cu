@@ -287,9 +287,11 @@ __device__ __forceinline__ float rows_finish(Ctx& c, const RowsInFlight& rf, uin
             const int g = min(ROW_GROUP, rf.n_live - r0);
             const uint8_t* rowp[ROW_GROUP];
             if (g4) {
-                c.ring.wait(slot0); TR(c, TR_ROWWAIT)   // a gathered group completes on its first slot's barrier; rows past the last read as zeros
 #pragma unroll
-                for (int r = 0; r < ROW_GROUP; ++r) rowp[r] = gp + r * stride;
+                for (int r = 0; r < ROW_GROUP; r += 4)
+                    if (r < g) { c.ring.wait(slot0 + r); TR(c, TR_ROWWAIT) }   // four gathered rows complete on their first slot's barrier; rows past the last read as zeros
+#pragma unroll
+                for (int r = 0; r < ROW_GROUP; ++r) rowp[r] = gp + (ROW_GROUP > 4 && r >= ((g + 3) & ~3) ? 0 : r) * stride;
             } else {
 #pragma unroll
                 for (int r = 0; r < ROW_GROUP; ++r) {
@@ -303,7 +305,7 @@ __device__ __forceinline__ float rows_finish(Ctx& c, const RowsInFlight& rf, uin
             const int mr = rf.rank - r0;
             const int nxt = mr - S;
             if (g4) {
-                if (rf.has && nxt == 0) c.ring.post_gather4(slot0, c.p.rows_tmap, s, rf.g1, rf.g2, rf.g3);
+                if (rf.has && nxt >= 0 && nxt < ROW_GROUP && (nxt & 3) == 0) c.ring.post_gather4(slot0 + nxt, c.p.rows_tmap, s, rf.g1, rf.g2, rf.g3);
             } else if (rf.has && nxt >= 0 && nxt < g) c.ring.post(slot0 + nxt, rf.grow, ix.row_stride);
             const float got = __shfl_sync(FULL, red, group_owner<ROW_GROUP>(mr & (ROW_GROUP - 1)));
             if (rf.has && mr >= 0 && mr < g) myraw = got;
@@ -1355,10 +1357,12 @@ size_t search_smem_per_warp(const SearchParams& p) {
 }
 
 typedef void (*search_kernel_t)(const SearchParams);
-// The kernel variant a call runs: the three row kinds, f32 warp rows without a ring (gathered directly), and the f32 ring
-// kernel compiled for one more resident CTA per SM (fewer registers) for rows whose rings leave room for it.
-constexpr int VAR_F32_RING_SHORT = 4, N_VARIANTS = 5;
+// The kernel variant a call runs: the three row kinds, f32 warp rows without a ring (gathered directly), the f32 ring
+// kernel compiled for one more resident CTA per SM (fewer registers) for rows whose rings leave room for it, and the binary
+// kernel compiled for four CTAs per SM (128 registers, nothing spilled) for heaps so large that shared memory holds no more.
+constexpr int VAR_F32_RING_SHORT = 4, VAR_BIN_WIDE = 5, N_VARIANTS = 6;
 static int variant_of(const SearchParams& p) {
+    if (p.ix.kind == KIND_BIN && p.bin_wide) return VAR_BIN_WIDE;
     if (p.ix.kind != KIND_F32_WARP) return p.ix.kind;
     if (p.ring_slots == 0) return KIND_F32_DIRECT;
     return p.ring_short ? VAR_F32_RING_SHORT : KIND_F32_WARP;
@@ -1369,6 +1373,7 @@ static search_kernel_t kernel_for(int variant) {
         case VAR_F32_RING_SHORT: return hnsw_search_kernel<KIND_F32_WARP, HB_MIN_BLOCKS_F32_SHORT>;
         case KIND_F32_DIRECT: return hnsw_search_kernel<KIND_F32_DIRECT, HB_MIN_BLOCKS_DIRECT>;
         case KIND_F32_LANE: return hnsw_search_kernel<KIND_F32_LANE, 4>;
+        case VAR_BIN_WIDE: return hnsw_search_kernel<KIND_BIN, 4>;
         default: return hnsw_search_kernel<KIND_BIN, HB_MIN_BLOCKS_BIN>;
     }
 }

@@ -74,6 +74,8 @@ __device__ __forceinline__ void topk_insert(u64* a, int& len, int cap, u64 key) 
 // the F words of a block come from MERGE_BLOCK independent warp reductions, then all loads of the block are issued, then
 // all its stores — one shared-memory round trip per block (2 tiles: measured best on all three workloads against 1, 3, 4 and 8).  Tiles below the
 // first insertion point are not touched.  Equivalent to inserting the keys one after the other (all keys are distinct).
+// (A fast path for tiles that hold no new key — they move by a constant — was measured and is not worth its test: +-0 at ef = 800,
+// -2 % on short heaps.)
 //   DESC   array is descending (search queue, next pop at the end) instead of ascending (result set)
 //   keep   final length is capped to `keep` (the entries that sort last are dropped)
 // Returns the new length.
