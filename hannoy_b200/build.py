@@ -18,7 +18,9 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # bit-exactness: no implicit FMA contraction, IEEE div/sqrt, no flush-to-zero
-    "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false", "-split-compile", "0",
+    "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+    # (no -split-compile: with it ptxas produced kernels of 8 296 or 9 144 instructions from the SAME source from one run to the
+    # next — and the larger one is ~10 % slower; a single-threaded compile of search.cu takes 26 s and is reproducible)
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function",
 ]
 VARIANTS = {"": [], "phases": ["-DHB_PHASES"], "trace": ["-DHB_TRACE"], "rg2": ["-DHB_ROW_GROUP=2"], "rg8": ["-DHB_ROW_GROUP=8"],
@@ -31,6 +33,8 @@ for _b in (4, 5, 6, 7, 8):   # dev: occupancy the binary / f32 ring kernels are 
 VARIANTS["nospec"] = ["-DHB_SPEC_VIS=0"]
 VARIANTS["nospecbin"] = ["-DHB_SPEC_VIS_BIN=0"]
 VARIANTS["nodedupe"] = ["-DHB_SPEC_DEDUPE=0"]
+VARIANTS["dedupef32"] = ["-DHB_SPEC_DEDUPE_F32=1"]
+VARIANTS["keep"] = ["-DHB_UPPER_KEEP=1"]
 for _g in (1, 2, 3, 8):
     VARIANTS[f"g{_g}"] = [f"-DHB_MERGE_BLOCK={_g}"]
 

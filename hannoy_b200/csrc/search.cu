@@ -46,6 +46,13 @@
 #ifndef HB_SPEC_VIS
 #define HB_SPEC_VIS 1      // prefetch the visited-set words of the expected next expansion's neighbours (C2 +10 %, C3 small batches +7 %)
 #endif
+#ifndef HB_UPPER_KEEP
+#define HB_UPPER_KEEP 1    // rows gathered on the upper layers are kept in L2 (evict_last: every query descends through the same few thousand
+                           // nodes), layer-0 rows stream through it (evict_first): C3 11.58 -> 11.36 ms, C2 5.22 -> 5.18 ms
+#endif
+#ifndef HB_SPEC_DEDUPE_F32
+#define HB_SPEC_DEDUPE_F32 0
+#endif
 #ifndef HB_SPEC_DEDUPE
 #define HB_SPEC_DEDUPE 1
 #endif
@@ -570,6 +577,9 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
     c.res_len = 0;
     c.q_len = 0;
     queue_rewind(c);
+#if HB_UPPER_KEEP
+    if (KIND == KIND_F32_WARP) c.ring.policy = level ? l2_policy_evict_last() : l2_policy_evict_first();
+#endif
     c.cur_dist = c.cur_exp = c.cur_deg = 0;
     const uint32_t* list = linear ? c.p.cand_slots : eps;
     const uint32_t n_first = linear ? c.p.n_cand_slots : (eps ? n_eps : 1u);
@@ -772,8 +782,8 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
         // the adjacency line requested ahead has landed by now: pull the visited-set words of ITS neighbours into L2, so that
         // the atomics of the next expansion — when it is the one expected — are answered by L2 instead of DRAM
         // (binary kernel: once per expected node — it stays the expected one for as long as freshly accepted points are popped ahead of
-        // it; the f32 kernels measure faster when the hint is repeated every expansion: C2 5.08 vs 5.67 ms, C3 single query 0.70 vs 0.78 ms)
-        if ((HB_SPEC_VIS_BIN || KIND != KIND_BIN) && nbrx && spec_cs != 0xffffffffu && (KIND != KIND_BIN || !HB_SPEC_DEDUPE || spec_cs != spec_pf)) {
+        // it; for the f32 kernels repeating the hint or not measures the same with reproducible builds)
+        if ((HB_SPEC_VIS_BIN || KIND != KIND_BIN) && nbrx && spec_cs != 0xffffffffu && ((KIND != KIND_BIN && !HB_SPEC_DEDUPE_F32) || !HB_SPEC_DEDUPE || spec_cs != spec_pf)) {
             if (spec_adj != 0xffffffffu) prefetch_l2(&c.vis[spec_adj >> 5]);
             spec_pf = spec_cs;
         }
