@@ -35,7 +35,7 @@ VARIANTS["nospecbin"] = ["-DHB_SPEC_VIS_BIN=0"]
 VARIANTS["nodedupe"] = ["-DHB_SPEC_DEDUPE=0"]
 VARIANTS["dedupef32"] = ["-DHB_SPEC_DEDUPE_F32=1"]
 VARIANTS["keep"] = ["-DHB_UPPER_KEEP=1"]
-for _g in (1, 2, 3, 8):
+for _g in (1, 2, 3, 4, 8):
     VARIANTS[f"g{_g}"] = [f"-DHB_MERGE_BLOCK={_g}"]
 
 

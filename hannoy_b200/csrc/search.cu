@@ -44,7 +44,8 @@
 #define HB_EARLY_ROWS 1  // layer-0 deferred pops: request the rows of an expansion before merging the previous chunk into the heaps
 #endif
 #ifndef HB_SPEC_VIS
-#define HB_SPEC_VIS 1      // prefetch the visited-set words of the expected next expansion's neighbours (C2 +10 %, C3 small batches +7 %)
+#define HB_SPEC_VIS 1      // prefetch the visited-set words of the expected next expansion's neighbours (f32 kernels; worth ~1 % on C2 — the
+                           // larger gains first measured for it were differences between two compilations of the same source, build.py)
 #endif
 #ifndef HB_UPPER_KEEP
 #define HB_UPPER_KEEP 1    // rows gathered on the upper layers are kept in L2 (evict_last: every query descends through the same few thousand
@@ -57,7 +58,7 @@
 #define HB_SPEC_DEDUPE 1
 #endif
 #ifndef HB_SPEC_VIS_BIN
-#define HB_SPEC_VIS_BIN 1  // ... in the binary kernel too
+#define HB_SPEC_VIS_BIN 0  // ... not in the binary kernel: +17 GB of DRAM reads per C4s launch (speculation that fails) for < 1 %
 #endif
 #ifndef HB_MIN_BLOCKS_F32
 #define HB_MIN_BLOCKS_F32 3  // resident CTAs per SM the f32 ring kernel is compiled for (register budget): long rows, shared memory allows no more
