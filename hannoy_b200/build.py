@@ -35,6 +35,9 @@ VARIANTS["nospecbin"] = ["-DHB_SPEC_VIS_BIN=0"]
 VARIANTS["nodedupe"] = ["-DHB_SPEC_DEDUPE=0"]
 VARIANTS["dedupef32"] = ["-DHB_SPEC_DEDUPE_F32=1"]
 VARIANTS["keep"] = ["-DHB_UPPER_KEEP=1"]
+VARIANTS["opaque"] = ["-DHB_OPAQUE_ADDR=1"]
+VARIANTS["share"] = ["-DHB_TEAM_SHARE=1"]
+VARIANTS["f32s5"] = ["-DHB_MIN_BLOCKS_F32_SHORT=5"]
 for _g in (1, 2, 3, 4, 8):
     VARIANTS[f"g{_g}"] = [f"-DHB_MERGE_BLOCK={_g}"]
 

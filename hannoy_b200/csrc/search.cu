@@ -47,6 +47,12 @@
 #define HB_SPEC_VIS 1      // prefetch the visited-set words of the expected next expansion's neighbours (f32 kernels; worth ~1 % on C2 — the
                            // larger gains first measured for it were differences between two compilations of the same source, build.py)
 #endif
+#ifndef HB_OPAQUE_ADDR
+#define HB_OPAQUE_ADDR 0
+#endif
+#ifndef HB_TEAM_SHARE
+#define HB_TEAM_SHARE 0
+#endif
 #ifndef HB_UPPER_KEEP
 #define HB_UPPER_KEEP 1    // rows gathered on the upper layers are kept in L2 (evict_last: every query descends through the same few thousand
                            // nodes), layer-0 rows stream through it (evict_first): C3 11.58 -> 11.36 ms, C2 5.22 -> 5.18 ms
@@ -791,6 +797,13 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
 #endif
         if (l01) PH_ADD(c, PH_ROWS)
         if (KIND == KIND_F32_WARP && helpers_used) dist = team_collect(c, lm, helpers_used, per, dist);
+#if HB_TEAM_SHARE
+        // dev: three walks and one helper in the CTA: the helper is held for one chunk at a time, so that it goes round the walks
+        if (KIND == KIND_F32_WARP && c.ts && (*c.team & 0xfu)) {
+            const uint32_t idle = ld_volatile_shared(&c.ts->n_idle);
+            if (2 * idle < (uint32_t)SEARCH_WARPS_PER_BLOCK) team_release(*c.ts, *c.team);
+        }
+#endif
         if (bail) break;
         const uint32_t bits = __float_as_uint(dist);
         if (l01) PH_ADD(c, PH_COLLECT)
@@ -1114,6 +1127,11 @@ __global__ void __launch_bounds__(SEARCH_WARPS_PER_BLOCK * 32, MIN_BLOCKS) hnsw_
     ring.stride = p.ring_stride;
     ring.phase = 0;
     ring.policy = l2_policy_evict_first();
+#if HB_OPAQUE_ADDR
+    // dev: per-warp addresses are pure functions of threadIdx and the parameters, so under register pressure the compiler may
+    // re-derive them at every use; made opaque, they are kept in registers or spilled once
+    asm volatile("" : "+l"(qs), "+l"(heap), "+l"(ring.ptr), "+r"(ring.data), "+r"(ring.bars));
+#endif
     if (p.ring_slots) {
         if (lane_id() == 0) {
             for (uint32_t i = 0; i < p.ring_slots; ++i) mbar_init(ring.bars + i * 8, 1);
