@@ -36,6 +36,8 @@ VARIANTS["nodedupe"] = ["-DHB_SPEC_DEDUPE=0"]
 VARIANTS["dedupef32"] = ["-DHB_SPEC_DEDUPE_F32=1"]
 VARIANTS["keep"] = ["-DHB_UPPER_KEEP=1"]
 VARIANTS["opaque"] = ["-DHB_OPAQUE_ADDR=1"]
+VARIANTS["nolean"] = ["-DHB_LEAN=0"]
+VARIANTS["visatom"] = ["-DHB_VIS_LOAD=0"]
 VARIANTS["share"] = ["-DHB_TEAM_SHARE=1"]
 VARIANTS["f32s5"] = ["-DHB_MIN_BLOCKS_F32_SHORT=5"]
 for _g in (1, 2, 3, 4, 8):

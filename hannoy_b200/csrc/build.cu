@@ -436,6 +436,7 @@ hb_status build_graph_on_device(hb_index* ix, uint32_t M, uint32_t M0, uint32_t 
     SearchParams& sp = bp.sp;
     sp.ix = d;
     sp.mode = 1;  // the query is a stored item
+    sp.vis_atomic = 1;  // a mutable list can name a neighbour twice (collapsed when the lists are written back)
     sp.count = efc; sp.ef_raw = efc;
     sp.q_smem_bytes = (d.row_stride + 15) & ~15u;
     sp.defer = tunable("defer", 1);

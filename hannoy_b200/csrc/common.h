@@ -91,6 +91,7 @@ struct SearchParams {
     uint32_t q_smem_bytes = 0;         // per-warp query staging bytes
     uint32_t ring_slots = 0;           // KIND_F32_WARP: rows in flight per warp (multiple of ROW_GROUP), ring.cuh
     uint32_t ring_stride = 0;          // bytes between ring slots
+    int vis_atomic = 0;                // graph builder: adjacency lists may hold duplicates, the visited test must serialise the lanes of a chunk
     int bin_wide = 0;                  // binary kernel: heaps so large (ef ~ 800) that shared memory limits the SM to four CTAs: the 128-register instantiation
     int ring_short = 0;                // short rows: the instantiation of the ring kernel compiled for one more resident CTA per SM
     // id-sharded search with the all-gather fused into the epilogue: every query's padded top-k is stored straight into

@@ -47,6 +47,12 @@
 #define HB_SPEC_VIS 1      // prefetch the visited-set words of the expected next expansion's neighbours (f32 kernels; worth ~1 % on C2 — the
                            // larger gains first measured for it were differences between two compilations of the same source, build.py)
 #endif
+#ifndef HB_VIS_LOAD
+#define HB_VIS_LOAD 1
+#endif
+#ifndef HB_LEAN
+#define HB_LEAN 1          // bookkeeping trimmed from the per-expansion chain: traversal counters only when asked for, the negative-distance
+#endif                     // test only for the one metric that can produce one, the prune test's invariants hoisted
 #ifndef HB_OPAQUE_ADDR
 #define HB_OPAQUE_ADDR 0
 #endif
@@ -113,6 +119,7 @@ struct Ctx {
     const float* qs; float qn;            // query (device layout) in shared memory, query header norm
     uint32_t excl;                        // by_item: slot removed from the candidates, else UINT32_MAX
     bool overflow;
+    bool trim_ok;                         // this visit may trim dead queue entries (pass 0, no poll-exact cancellation, no negative distances expected)
     bool cancelled;                       // the visit in progress returned Completion::Cancelled(res)
     uint32_t polls;                       // calls of cancel_fn made by this query so far
     bool tr;                              // this warp writes the event trace (HB_TRACE builds)
@@ -157,7 +164,16 @@ enum ChunkMode { CH_EP, CH_NBR, CH_LINEAR };
 // ---- visited set --------------------------------------------------------------------------------------
 // `path.insert(point)` in two halves so that independent work can sit between the atomic and its use:
 // vis_issue sends the atomicOr (returns the old word), vis_finish turns it into `fresh` and logs the touched slots.
+// HB_VIS_LOAD: the word is READ (L2, bypassing L1) and only the lanes whose point is fresh set their bit afterwards, with a
+// reduction that returns nothing — a lookup of an already visited point (more than half of them) then leaves its sector clean,
+// where an atomicOr dirties it whatever the answer and costs a 32-byte write-back.  The bitset is this warp's alone; the
+// __syncwarp after the reductions orders them before the next chunk's reads by other lanes.
+// (Not in the graph builder: its mutable lists may name a neighbour twice, and only the atomic's serialisation tells the two
+// lanes of one chunk apart — SearchParams::vis_atomic.)
 __device__ __forceinline__ uint32_t vis_issue(Ctx& c, uint32_t s, bool valid) {
+#if HB_VIS_LOAD
+    if (!c.p.vis_atomic) return valid ? __ldcg(&c.vis[s >> 5]) : 0xffffffffu;
+#endif
     return valid ? atomicOr(&c.vis[s >> 5], 1u << (s & 31)) : 0xffffffffu;
 }
 // vis_finish leaves the slot's place in the touched list in `log_at` (UINT32_MAX: nothing to log); the store itself
@@ -165,6 +181,12 @@ __device__ __forceinline__ uint32_t vis_issue(Ctx& c, uint32_t s, bool valid) {
 // release at CTA scope, and it would otherwise wait for this global store to be acknowledged.
 __device__ __forceinline__ bool vis_finish(Ctx& c, uint32_t s, bool valid, uint32_t old, uint32_t& log_at) {
     const bool fresh = valid && !((old >> (s & 31)) & 1u);
+#if HB_VIS_LOAD
+    if (!c.p.vis_atomic) {
+        if (fresh) atomicOr(&c.vis[s >> 5], 1u << (s & 31));   // result unused: a reduction
+        __syncwarp();
+    }
+#endif
     unsigned m = __ballot_sync(FULL, fresh);
     log_at = 0xffffffffu;
     if (m) {
@@ -533,7 +555,7 @@ __device__ __forceinline__ void queue_rewind(Ctx& c) {
 __device__ __forceinline__ void heaps_stage_queue(Ctx& c, const ChunkUpdate& u, int ef) {
     if (u.mode == CH_LINEAR || c.overflow) return;
     const int lane = lane_id();
-    const bool prune = c.p.pass == 0 && !c.p.cancel_after && !c.p.no_trim && c.res_len >= ef && c.res_len > 0 && !(c.res[c.res_len - 1] >> 63);
+    const bool prune = (HB_LEAN ? c.trim_ok : (c.p.pass == 0 && !c.p.cancel_after && !c.p.no_trim)) && c.res_len >= ef && c.res_len > 0 && !(c.res[c.res_len - 1] >> 63);
     const uint32_t mb = prune ? (uint32_t)(c.res[c.res_len - 1] >> 32) : 0xffffffffu;
     if (prune && c.q_len > 0 && (uint32_t)(c.que[0] >> 32) > mb) {
         int lo = 1, hi = c.q_len;                  // first entry that is not dead (warp-uniform search)
@@ -597,6 +619,8 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
     const uint32_t xstride = ix.nbr0_stride;                 // 32, or 64: a full first line is followed by the second one
     uint32_t cont_cs = 0;                                    // node whose fixed-stride list is being continued (csr_pos = 32, csr_end = xstride)
     const bool defer = nbrx && c.p.pass == 0 && c.p.defer && !linear && !c.p.no_trim;  // a linear scan pops nothing (reader.rs:683-705)
+    const bool chk_neg = !linear && c.p.pass == 0 && !c.p.no_trim;   // trimming is only argued for non-negative distances (is_dead)
+    c.trim_ok = c.p.pass == 0 && !c.p.cancel_after && !c.p.no_trim;
     uint32_t spec_cs = 0xffffffffu, spec_adj = 0xffffffffu;  // adjacency line requested ahead of its pop
     uint32_t spec_pf = 0xffffffffu;                          // node whose neighbours' visited-set words were already prefetched
     uint32_t csr_pos = 0, csr_end = 0;                       // rest of the CSR list being expanded
@@ -727,7 +751,7 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
                 valid = s != 0xffffffffu;
                 if (!valid) s = 0;
             }
-            c.cur_deg += __popc(__ballot_sync(FULL, valid));
+            if (!HB_LEAN || c.p.out_ctr) c.cur_deg += __popc(__ballot_sync(FULL, valid));
             if (l01) PH_ADD(c, PH_ADJ)
             TR(c, TR_ADJ)
         }
@@ -748,7 +772,7 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
         int per = 32;
         RowsInFlight rf;
         if (lm) {
-            c.cur_dist += __popc(lm);
+            if (!HB_LEAN || c.p.out_ctr) c.cur_dist += __popc(lm);
             if (KIND == KIND_F32_WARP && c.ts) {
                 team_update(c);
                 const int H = __popc(*c.team & 0xfu), n_live = __popc(lm);
@@ -807,7 +831,7 @@ __device__ __forceinline__ void visit(Ctx& c, const uint32_t* eps, uint32_t n_ep
         if (bail) break;
         const uint32_t bits = __float_as_uint(dist);
         if (l01) PH_ADD(c, PH_COLLECT)
-        if (mode != CH_LINEAR && c.p.pass == 0 && !c.p.no_trim && __ballot_sync(FULL, live && (bits >> 31))) { c.overflow = true; break; }
+        if ((HB_LEAN ? chk_neg : (mode != CH_LINEAR && c.p.pass == 0 && !c.p.no_trim)) && __any_sync(FULL, live && (bits >> 31))) { c.overflow = true; break; }
         // ---- which points are accepted, and which of those may enter the result set (reader.rs:322,353,355-359) ----
         const bool pf = live && passes_filter(c, s, filt);
         bool acc = live;
