@@ -220,6 +220,20 @@ class Reader {
         if (hb_index_item_vector(ix_, item, v.data()) != HB_OK) return std::nullopt;
         return v;
     }
+    // Replicas on further GPUs (hb_index_replicate): from then on ONE by_vector / by_item batch is partitioned into contiguous
+    // slices, one host thread + stream per device — the reference's rayon workers over one Reader (src/parallel.rs:18-38).
+    void replicate(const std::vector<int>& devices) { check(hb_index_replicate(ix_, devices.data(), (int)devices.size())); }
+    int n_devices() const { return hb_index_n_devices(ix_); }
+    // The graph as CSR over item ids (Reader::get_links for every item of a layer at once, reader.rs:966-976).
+    uint32_t n_layers() const { return hb_index_n_layers(ix_); }
+    std::pair<std::vector<uint64_t>, std::vector<uint32_t>> layer_csr(uint32_t layer) const {
+        uint64_t nnz = 0;
+        std::vector<uint64_t> off(n_items() + 1);
+        check(hb_index_layer_csr(ix_, layer, off.data(), nullptr, 0, &nnz));
+        std::vector<uint32_t> nbr(nnz);
+        check(hb_index_layer_csr(ix_, layer, off.data(), nbr.data(), nnz, &nnz));
+        return {std::move(off), std::move(nbr)};
+    }
     QueryBuilder<D> nns(size_t count) const { return QueryBuilder<D>(this, count); }
     const hb_index* raw() const { return ix_; }
 
